@@ -1,0 +1,217 @@
+"""ctypes binding of libdicegp.so (the C ABI in include/dicegp.h).
+
+The product path has no CPU fallback: if the shared library is missing or no CUDA device
+is present, every entry point raises -- loudly -- instead of computing on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdicegp.so")
+
+ABI_VERSION = 1
+
+CHAIN_RUNNING, CHAIN_CONVERGED, CHAIN_EXHAUSTED = 0, 1, 2
+
+# every symbol include/dicegp.h declares (tests check that the library exports all of them)
+SYMBOLS = (
+    "dicegp_abi_version", "dicegp_create", "dicegp_destroy", "dicegp_last_error",
+    "dicegp_get_limits", "dicegp_upload_genes", "dicegp_set_chains",
+    "dicegp_main_chains_from_prerun", "dicegp_run_host_stream", "dicegp_run_device_stream",
+    "dicegp_chain_status", "dicegp_download_trace", "dicegp_posterior_summary",
+    "dicegp_last_run_stats",
+)
+
+
+class DiceGPError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("libdicegp error %d: %s" % (code, text))
+        self.code = code
+
+
+class ChainDesc(C.Structure):
+    """struct dicegp_chain_desc"""
+    _fields_ = [
+        ("gene", C.c_int32), ("t0", C.c_int32), ("Tc", C.c_int32),
+        ("M", C.c_int32), ("initial", C.c_int32), ("gap", C.c_int32),
+        ("kinv_off", C.c_int64), ("prop_factor_off", C.c_int64),
+        ("jump_scale_off", C.c_int64), ("jump_const_off", C.c_int64),
+        ("y0_off", C.c_int64), ("prior_const", C.c_double),
+    ]
+
+
+class Limits(C.Structure):
+    _fields_ = [("max_isoforms", C.c_int32), ("max_times", C.c_int32),
+                ("abi_version", C.c_int32), ("sm_count", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """dlopen libdicegp.so and declare prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libdicegp.so is not built (%s). Run `python -c 'import __graft_entry__ as g; "
+            "g.build()'` or `make -C diceseq_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    pi32, pi64, pd = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
+    lib.dicegp_abi_version.restype = C.c_int
+    lib.dicegp_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.dicegp_destroy.argtypes = [vp]
+    lib.dicegp_last_error.argtypes = [vp]
+    lib.dicegp_last_error.restype = C.c_char_p
+    lib.dicegp_get_limits.argtypes = [vp, C.POINTER(Limits)]
+    lib.dicegp_upload_genes.argtypes = [vp, i32, i32, pi32, pi32, pd, i64, pd, i64]
+    lib.dicegp_set_chains.argtypes = [vp, i32, C.POINTER(ChainDesc), pd, i64]
+    lib.dicegp_main_chains_from_prerun.argtypes = [vp, i32, i32, i32, dbl, pd, pd, dbl, pd]
+    lib.dicegp_run_host_stream.argtypes = [vp, i32, pi32, i32, pd, pi64, i64, pd]
+    lib.dicegp_run_device_stream.argtypes = [vp, C.c_uint64, pi64]
+    lib.dicegp_chain_status.argtypes = [vp, i32, pi32, pi32, pi32, pi32, pi32, pi32]
+    lib.dicegp_download_trace.argtypes = [vp, i32, i32, i32, pd, pd, pd, pd]
+    lib.dicegp_posterior_summary.argtypes = [vp, i32, pi32, pd, pd, pi64, pd]
+    lib.dicegp_last_run_stats.argtypes = [vp, pd, pi64, pi64, pi64]
+    for name in SYMBOLS:
+        if name != "dicegp_last_error":
+            getattr(lib, name).restype = C.c_int
+    if lib.dicegp_abi_version() != ABI_VERSION:
+        raise ImportError("libdicegp.so ABI %d != binding ABI %d" % (lib.dicegp_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def _p(arr, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype)) if arr is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+class Context:
+    """One handle per GPU (dicegp_create / dicegp_destroy)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self._h = C.c_void_p()
+        rc = self.lib.dicegp_create(int(device), C.byref(self._h))
+        if rc != 0:
+            raise DiceGPError(rc, self.lib.dicegp_last_error(None).decode())
+        self.device = device
+        self.gene_C = None
+        self.T = 0
+        self.chain_shapes = []      # (C, Tc, M) per chain
+
+    def close(self):
+        if self._h:
+            self.lib.dicegp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise DiceGPError(rc, self.lib.dicegp_last_error(self._h).decode())
+
+    def limits(self):
+        lim = Limits()
+        self._check(self.lib.dicegp_get_limits(self._h, C.byref(lim)))
+        return lim
+
+    # -- genes ---------------------------------------------------------------------------
+    def upload_genes(self, packed):
+        """packed: diceseq_b200.packer.PackedGenes"""
+        n_iso, n_reads = _i32(packed.n_iso), _i32(packed.n_reads)
+        W, lens = _f64(packed.W), _f64(packed.len_iso)
+        self._check(self.lib.dicegp_upload_genes(
+            self._h, packed.G, packed.T, _p(n_iso, C.c_int32), _p(n_reads, C.c_int32),
+            _p(W, C.c_double), W.size, _p(lens, C.c_double), lens.size))
+        self.gene_C = n_iso.copy()
+        self.T = packed.T
+        self.chain_shapes = []
+
+    # -- chains --------------------------------------------------------------------------
+    def set_chains(self, descs, pool):
+        arr = (ChainDesc * len(descs))(*descs)
+        pool = _f64(pool)
+        self._check(self.lib.dicegp_set_chains(self._h, len(descs), arr, _p(pool, C.c_double), pool.size))
+        self.chain_shapes = [(int(self.gene_C[d.gene]), d.Tc, d.M) for d in descs]
+
+    def main_chains_from_prerun(self, M, initial, gap, theta1, kinv, prop_factor, prior_const):
+        kinv = _f64(kinv)
+        pf = _f64(prop_factor) if prop_factor is not None else None
+        G = len(self.gene_C)
+        var = np.zeros((G, self.limits().max_isoforms))
+        self._check(self.lib.dicegp_main_chains_from_prerun(
+            self._h, M, initial, gap, float(theta1), _p(kinv, C.c_double),
+            _p(pf, C.c_double), float(prior_const), _p(var, C.c_double)))
+        self.chain_shapes = [(int(c), self.T, M) for c in self.gene_C]
+        return var
+
+    # -- running -------------------------------------------------------------------------
+    def run_host_stream(self, chain_ids, n_steps, delta, delta_off, u):
+        ids, doff = _i32(chain_ids), _i64(delta_off)
+        delta, u = _f64(delta), _f64(u)
+        assert u.size == ids.size * n_steps
+        self._check(self.lib.dicegp_run_host_stream(
+            self._h, ids.size, _p(ids, C.c_int32), int(n_steps), _p(delta, C.c_double),
+            _p(doff, C.c_int64), delta.size, _p(u, C.c_double)))
+
+    def run_device_stream(self, seed, stream_id=None):
+        sid = _i64(stream_id) if stream_id is not None else None
+        self._check(self.lib.dicegp_run_device_stream(self._h, C.c_uint64(int(seed)), _p(sid, C.c_int64)))
+
+    # -- results -------------------------------------------------------------------------
+    def chain_status(self, chain_ids=None):
+        if chain_ids is None:
+            chain_ids = np.arange(len(self.chain_shapes))
+        ids = _i32(chain_ids)
+        out = [np.zeros(ids.size, dtype=np.int32) for _ in range(5)]
+        self._check(self.lib.dicegp_chain_status(self._h, ids.size, _p(ids, C.c_int32),
+                                                 *[_p(o, C.c_int32) for o in out]))
+        return dict(zip(("m", "n_rows", "cnt", "state", "flags"), out))
+
+    def download_trace(self, chain, n_rows, first_row=0):
+        Cn, Tc, _M = self.chain_shapes[chain]
+        psi = np.empty((n_rows, Cn, Tc))
+        y = np.empty((n_rows, Cn, Tc))
+        pro = np.empty(n_rows)
+        lik = np.empty(n_rows)
+        self._check(self.lib.dicegp_download_trace(
+            self._h, int(chain), int(first_row), int(n_rows), _p(psi, C.c_double),
+            _p(y, C.c_double), _p(pro, C.c_double), _p(lik, C.c_double)))
+        return psi, y, pro, lik
+
+    def last_run_stats(self):
+        ms = C.c_double()
+        launches, evals, steps = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.dicegp_last_run_stats(self._h, C.byref(ms), C.byref(launches),
+                                                   C.byref(evals), C.byref(steps)))
+        return {"kernel_ms": ms.value, "launches": launches.value, "read_evals": evals.value,
+                "steps": steps.value}

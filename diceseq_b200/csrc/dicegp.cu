@@ -1,0 +1,769 @@
+// dicegp.cu -- kernels' global entry points and the C ABI declared in include/dicegp.h.
+//
+// Host side: device tables for genes and chains, launch classes (which chains run with W
+// resident in shared memory at which occupancy, which stream W from L2/HBM), host- and
+// device-generated stream drivers, status / trace download.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dicegp.h"
+
+namespace dg {
+constexpr int DICEGP_CHAIN_CONVERGED_ = 1;
+constexpr int DICEGP_CHAIN_EXHAUSTED_ = 2;
+}  // namespace dg
+#include "dicegp_chain.cuh"
+
+// =======================================================================================
+// kernels
+// =======================================================================================
+// Static assignment (queue == nullptr): block b advances chain ids[b].
+// Persistent (queue != nullptr): blocks pull slots from an atomic counter until empty;
+// ids are sorted by decreasing cost so the heavy chains start first.
+template <bool W_IN_SMEM>
+__global__ void __launch_bounds__(DG_MAXTHREADS, 1)
+dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__restrict__ ids, int n_ids,
+                    int n_steps, int use_tma, int *queue) {
+    extern __shared__ __align__(128) double dg_smem[];
+    if (queue == nullptr) {
+        const int slot = blockIdx.x;
+        if (slot < n_ids) dg::run_chain<W_IN_SMEM>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma);
+        return;
+    }
+    __shared__ int next_slot;
+    while (true) {
+        if (threadIdx.x == 0) next_slot = atomicAdd(queue, 1);
+        __syncthreads();
+        const int slot = next_slot;
+        __syncthreads();
+        if (slot >= n_ids) break;
+        dg::run_chain<W_IN_SMEM>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma);
+        __syncthreads();
+    }
+}
+
+// numpy pairwise sum (n <= 128) over a strided global series, used where the reference
+// reduces a 1-D view (np.var of a (rows,1) slice collapses to 1-D and goes pairwise).
+__device__ double dg_pw_global(const double *v, int n, size_t stride) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += v[i * stride];
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = v[j * stride];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += v[(i + j) * stride];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += v[i * stride];
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return dg_pw_global(v, n2, stride) + dg_pw_global(v + n2 * stride, n - n2, stride);
+}
+
+// Jump variance from the pre-runs (run_utils.py:111-116).  One thread per (gene, isoform):
+//   var[c] = (sum_j np.var(Y_j[int(m_j/4):, c, 0]) + 1e-6) / T
+// np.var(axis=0) of the (rows, C-1) slice adds rows sequentially, except that a (rows, 1)
+// slice (C == 2) collapses to 1-D and is summed pairwise (probed on numpy 2.3.5).
+__global__ void dicegp_prerun_var_kernel(GeneTab gt, ChainTab ct, int G, double *__restrict__ var_out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = idx / DG_MAXC, c = idx % DG_MAXC;
+    if (g >= G) return;
+    const int C = gt.C[g], T = gt.T;
+    if (c >= C - 1) { var_out[(size_t)g * DG_MAXC + c] = 0.0; return; }
+    double acc = 0.0;
+    for (int j = 0; j < T; ++j) {
+        const int chain = g * T + j;
+        const int state = ct.state[chain];
+        const int m_ret = ct.m_ret[chain];
+        const int n_rows = (state == dg::DICEGP_CHAIN_CONVERGED_) ? m_ret : ct.M[chain];
+        const int b = (int)((double)m_ret / 4.0);
+        const int n = n_rows - b;
+        const int rowlen = 2 * C + 2;                       // Tc == 1
+        const double *y = ct.trace + ct.trace_off[chain] + (size_t)b * rowlen + C + c;
+        double mean, ss;
+        if (C == 2) {
+            mean = dg_pw_global(y, n, rowlen) / (double)n;
+            // pairwise over squared deviations: small n (76), do it through a local copy
+            double d[128];
+            if (n <= 128) {
+                for (int i = 0; i < n; ++i) { double e = y[(size_t)i * rowlen] - mean; d[i] = e * e; }
+                ss = dg_pw_global(d, n, 1);
+            } else {
+                ss = 0.0;
+                for (int i = 0; i < n; ++i) { double e = y[(size_t)i * rowlen] - mean; ss += e * e; }
+            }
+        } else {
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) s += y[(size_t)i * rowlen];
+            mean = s / (double)n;
+            ss = 0.0;
+            for (int i = 0; i < n; ++i) { double e = y[(size_t)i * rowlen] - mean; ss += e * e; }
+        }
+        acc += ss / (double)n;
+    }
+    var_out[(size_t)g * DG_MAXC + c] = (acc + 0.000001) / (double)T;
+}
+
+// =======================================================================================
+// host context
+// =======================================================================================
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t resize(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct LaunchClass {
+    int threads;
+    size_t smem_limit;      // dynamic shared memory per block
+    int blocks_per_sm;
+    bool w_in_smem;
+};
+
+}  // namespace
+
+struct dicegp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaStream_t class_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[5] = {};
+    int use_tma = 1;
+
+    // genes
+    int G = 0, T = 0;
+    std::vector<int32_t> hC, hncnt, hroff;
+    std::vector<int64_t> hwoff, hlenoff;
+    DevBuf<int32_t> dC, dncnt, droff;
+    DevBuf<int64_t> dwoff, dlenoff;
+    DevBuf<double> dW, dlen;
+
+    // chains
+    int n_chains = 0;
+    std::vector<dicegp_chain_desc> hdesc;
+    std::vector<int64_t> htrace_off, hst_off;
+    std::vector<int32_t> hchainC;
+    DevBuf<int32_t> cgene, ct0, cTc, cM, cinit, cgap, cm_next, ccnt, cstate, cm_ret, cflags;
+    DevBuf<int64_t> ckinv, cpf, cjs, cjc, cy0, ctrace_off, cst_off, cstream_id;
+    DevBuf<double> cprior, cpool, ctrace, cst;
+    bool have_stream_id = false;
+
+    // run scratch
+    DevBuf<int32_t> dids;
+    DevBuf<int64_t> ddoff;
+    DevBuf<double> ddelta, du, dvar;
+    DevBuf<int> dqueue;
+    double last_ms = 0.0;
+    int64_t last_launches = 0, last_evals = 0, last_steps = 0;
+    std::vector<int32_t> hm_next_before;
+
+    int fail(int code, const std::string &msg) {
+        err = msg;
+        g_last_error = msg;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char *what) {
+        return fail(DICEGP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    }
+};
+
+#define DG_CUDA(ctx, call)                                              \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return (ctx)->cuda_fail(e__, #call);    \
+    } while (0)
+
+namespace {
+
+GeneTab make_gene_tab(dicegp_ctx *c) {
+    GeneTab g;
+    g.C = c->dC.p; g.woff = c->dwoff.p; g.roff = c->droff.p; g.ncnt = c->dncnt.p;
+    g.lenoff = c->dlenoff.p; g.W = c->dW.p; g.len = c->dlen.p; g.T = c->T;
+    return g;
+}
+ChainTab make_chain_tab(dicegp_ctx *c) {
+    ChainTab t;
+    t.gene = c->cgene.p; t.t0 = c->ct0.p; t.Tc = c->cTc.p; t.M = c->cM.p; t.initial = c->cinit.p;
+    t.gap = c->cgap.p; t.kinv_off = c->ckinv.p; t.pf_off = c->cpf.p; t.js_off = c->cjs.p;
+    t.jc_off = c->cjc.p; t.y0_off = c->cy0.p; t.prior_const = c->cprior.p; t.pool = c->cpool.p;
+    t.trace_off = c->ctrace_off.p; t.st_off = c->cst_off.p;
+    t.stream_id = c->have_stream_id ? c->cstream_id.p : nullptr;
+    t.trace = c->ctrace.p; t.st = c->cst.p; t.m_next = c->cm_next.p; t.cnt = c->ccnt.p;
+    t.state = c->cstate.p; t.m_ret = c->cm_ret.p; t.flags = c->cflags.p;
+    return t;
+}
+
+// launch classes: W resident at 8/4/2/1 blocks per SM, then the streaming class
+void launch_classes(const dicegp_ctx *c, LaunchClass out[5]) {
+    const size_t per_sm = 233472;  // 228 KB
+    const int bps[4] = {8, 4, 2, 1};
+    const int thr[4] = {128, 256, 512, 1024};
+    for (int i = 0; i < 4; ++i) {
+        size_t lim = per_sm / bps[i] - 1024;
+        if (lim > c->smem_optin) lim = c->smem_optin;
+        out[i] = {thr[i], lim, bps[i], true};
+    }
+    out[4] = {512, 0, 2, false};
+}
+
+size_t fixed_smem_bytes(int C, int Tc, int threads) {
+    return (size_t)dg_layout(C, Tc, (threads + 31) / 32).total * sizeof(double);
+}
+
+int64_t chain_reads(const dicegp_ctx *c, int chain) {
+    const dicegp_chain_desc &d = c->hdesc[chain];
+    int64_t n = 0;
+    for (int t = 0; t < d.Tc; ++t) n += c->hncnt[(size_t)d.gene * c->T + d.t0 + t];
+    return n;
+}
+int64_t chain_wbytes(const dicegp_ctx *c, int chain) {
+    const dicegp_chain_desc &d = c->hdesc[chain];
+    const int32_t *ro = c->hroff.data() + (size_t)d.gene * (c->T + 1) + d.t0;
+    return (int64_t)c->hC[d.gene] * (ro[d.Tc] - ro[0]) * 8;
+}
+
+int pick_class(const dicegp_ctx *c, const LaunchClass cls[5], int chain) {
+    const dicegp_chain_desc &d = c->hdesc[chain];
+    const int C = c->hC[d.gene];
+    const int64_t wb = chain_wbytes(c, chain);
+    for (int i = 0; i < 4; ++i) {
+        if (cls[i].threads < C * d.Tc) continue;
+        if (fixed_smem_bytes(C, d.Tc, cls[i].threads) + (size_t)wb <= cls[i].smem_limit) return i;
+    }
+    return 4;
+}
+
+template <bool W_IN_SMEM>
+cudaError_t launch_chain_kernel(dicegp_ctx *c, const LaunchClass &lc, size_t smem, int grid,
+                                cudaStream_t st, const GeneTab &gt, const ChainTab &ct,
+                                const StreamArgs &sa, const int32_t *ids, int n_ids, int n_steps,
+                                int *queue) {
+    auto kern = dicegp_chain_kernel<W_IN_SMEM>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, lc.threads, smem, st>>>(gt, ct, sa, ids, n_ids, n_steps, c->use_tma, queue);
+    return cudaGetLastError();
+}
+
+// Common driver: advance `ids` (host order) by n_steps with stream args `sa`.
+// slot_of[i] gives the host-stream slot of ids[i] (host mode) -- the kernel's slot is the
+// position in the per-class id list, so the per-slot offsets are permuted alongside.
+int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, StreamArgs sa,
+               const std::vector<int64_t> *delta_off, bool persistent) {
+    LaunchClass cls[5];
+    launch_classes(c, cls);
+    std::vector<int32_t> by_class[5];
+    std::vector<int32_t> slot_src[5];
+    for (size_t i = 0; i < ids.size(); ++i) {
+        int k = pick_class(c, cls, ids[i]);
+        by_class[k].push_back(ids[i]);
+        slot_src[k].push_back((int32_t)i);
+    }
+    if (persistent) {
+        // heavy chains first (cost ~ C * reads)
+        for (int k = 0; k < 5; ++k) {
+            std::vector<std::pair<int64_t, int32_t>> key;
+            for (int32_t id : by_class[k]) key.push_back({-chain_wbytes(c, id), id});
+            std::sort(key.begin(), key.end());
+            for (size_t i = 0; i < key.size(); ++i) by_class[k][i] = key[i].second;
+        }
+    }
+    // flatten ids (and permuted host-stream offsets) into one device array
+    std::vector<int32_t> flat;
+    std::vector<int64_t> flat_doff;   // [0, n): delta offsets, [n, 2n): u offsets, kernel-slot order
+    std::vector<int64_t> flat_uoff;
+    size_t base[6] = {0};
+    for (int k = 0; k < 5; ++k) {
+        base[k] = flat.size();
+        for (size_t i = 0; i < by_class[k].size(); ++i) {
+            flat.push_back(by_class[k][i]);
+            if (delta_off) {
+                flat_doff.push_back((*delta_off)[slot_src[k][i]]);
+                flat_uoff.push_back((int64_t)slot_src[k][i] * n_steps);
+            }
+        }
+    }
+    base[5] = flat.size();
+    DG_CUDA(c, c->dids.resize(flat.size()));
+    DG_CUDA(c, cudaMemcpyAsync(c->dids.p, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if (delta_off) {
+        flat_doff.insert(flat_doff.end(), flat_uoff.begin(), flat_uoff.end());
+        DG_CUDA(c, c->ddoff.resize(flat_doff.size()));
+        DG_CUDA(c, cudaMemcpyAsync(c->ddoff.p, flat_doff.data(), flat_doff.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    DG_CUDA(c, c->dqueue.resize(8));
+    DG_CUDA(c, cudaMemsetAsync(c->dqueue.p, 0, 8 * sizeof(int), c->stream));
+
+    // steps bookkeeping for the stats (m_next before)
+    c->hm_next_before.resize(c->n_chains);
+    DG_CUDA(c, cudaMemcpyAsync(c->hm_next_before.data(), c->cm_next.p, c->n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+
+    GeneTab gt = make_gene_tab(c);
+    ChainTab ct = make_chain_tab(c);
+    DG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    DG_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+    int64_t launches = 0;
+    for (int k = 0; k < 5; ++k) {
+        const int n_ids = (int)by_class[k].size();
+        if (n_ids == 0) continue;
+        // dynamic shared memory of this launch: the largest need among its chains
+        size_t smem = 0;
+        for (int32_t id : by_class[k]) {
+            const dicegp_chain_desc &d = c->hdesc[id];
+            size_t need = fixed_smem_bytes(c->hC[d.gene], d.Tc, cls[k].threads);
+            if (cls[k].w_in_smem) need += (size_t)chain_wbytes(c, id);
+            smem = std::max(smem, need);
+        }
+        smem = (smem + 127) & ~(size_t)127;
+        if (smem > c->smem_optin) return c->fail(DICEGP_ERR_LIMIT, "chain needs more shared memory than the device offers");
+        cudaStream_t st = c->class_stream[k];
+        DG_CUDA(c, cudaStreamWaitEvent(st, c->ev_fork, 0));
+        StreamArgs sak = sa;
+        if (delta_off) {
+            sak.delta_off = c->ddoff.p + base[k];
+            sak.u_off = c->ddoff.p + flat.size() + base[k];
+        }
+        int grid = n_ids;
+        int *queue = nullptr;
+        if (persistent) {
+            grid = std::min(n_ids, c->sm_count * cls[k].blocks_per_sm);
+            queue = c->dqueue.p + k;
+        }
+        cudaError_t e;
+        if (cls[k].w_in_smem)
+            e = launch_chain_kernel<true>(c, cls[k], smem, grid, st, gt, ct, sak, c->dids.p + base[k], n_ids, n_steps, queue);
+        else
+            e = launch_chain_kernel<false>(c, cls[k], smem, grid, st, gt, ct, sak, c->dids.p + base[k], n_ids, n_steps, queue);
+        if (e != cudaSuccess) return c->cuda_fail(e, "chain kernel launch");
+        ++launches;
+        DG_CUDA(c, cudaEventRecord(c->ev_join[k], st));
+        DG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[k], 0));
+    }
+    DG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    DG_CUDA(c, cudaStreamSynchronize(c->stream));
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return c->cuda_fail(e, "chain kernel");
+    }
+    float ms = 0.f;
+    DG_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    // stats: steps advanced and read evaluations
+    std::vector<int32_t> after(c->n_chains);
+    DG_CUDA(c, cudaMemcpy(after.data(), c->cm_next.p, c->n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    int64_t steps = 0, evals = 0;
+    for (int32_t id : ids) {
+        int64_t ds = (int64_t)after[id] - c->hm_next_before[id];
+        int64_t init_eval = (c->hm_next_before[id] == 0 && after[id] > 0) ? 1 : 0;
+        steps += ds;
+        evals += (ds + init_eval) * chain_reads(c, id);
+    }
+    c->last_ms = ms; c->last_launches = launches; c->last_evals = evals; c->last_steps = steps;
+    return DICEGP_OK;
+}
+
+}  // namespace
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+extern "C" {
+
+int dicegp_abi_version(void) { return DICEGP_ABI_VERSION; }
+
+const char *dicegp_last_error(const dicegp_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : g_last_error.c_str();
+}
+
+int dicegp_create(int device, dicegp_ctx **out) {
+    if (!out) { g_last_error = "out is NULL"; return DICEGP_ERR_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_last_error = std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return DICEGP_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_last_error = "device index out of range"; return DICEGP_ERR_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return DICEGP_ERR_CUDA; }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return DICEGP_ERR_CUDA; }
+    if (prop.major < 10) {
+        g_last_error = "libdicegp is built for sm_100a (B200) only";
+        return DICEGP_ERR_CUDA;
+    }
+    dicegp_ctx *c = new dicegp_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    const char *no_tma = getenv("DICEGP_NO_TMA");
+    c->use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) goto fail;
+    for (int k = 0; k < 5; ++k) {
+        if (cudaStreamCreateWithFlags(&c->class_stream[k], cudaStreamNonBlocking) != cudaSuccess) goto fail;
+        if (cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) goto fail;
+    }
+    if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) goto fail;
+    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) goto fail;
+    *out = c;
+    return DICEGP_OK;
+fail:
+    g_last_error = std::string("stream/event creation failed: ") + cudaGetErrorString(cudaGetLastError());
+    delete c;
+    return DICEGP_ERR_CUDA;
+}
+
+int dicegp_destroy(dicegp_ctx *c) {
+    if (!c) return DICEGP_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->dC.release(); c->dncnt.release(); c->droff.release(); c->dwoff.release(); c->dlenoff.release();
+    c->dW.release(); c->dlen.release();
+    c->cgene.release(); c->ct0.release(); c->cTc.release(); c->cM.release(); c->cinit.release();
+    c->cgap.release(); c->cm_next.release(); c->ccnt.release(); c->cstate.release(); c->cm_ret.release();
+    c->cflags.release(); c->ckinv.release(); c->cpf.release(); c->cjs.release(); c->cjc.release();
+    c->cy0.release(); c->ctrace_off.release(); c->cst_off.release(); c->cstream_id.release();
+    c->cprior.release(); c->cpool.release(); c->ctrace.release(); c->cst.release();
+    c->dids.release(); c->ddoff.release(); c->ddelta.release(); c->du.release(); c->dvar.release();
+    c->dqueue.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int k = 0; k < 5; ++k) {
+        if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+        if (c->class_stream[k]) cudaStreamDestroy(c->class_stream[k]);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return DICEGP_OK;
+}
+
+int dicegp_get_limits(const dicegp_ctx *ctx, dicegp_limits *out) {
+    if (!out) return DICEGP_ERR_ARG;
+    out->max_isoforms = DG_MAXC;
+    out->max_times = DG_MAXT;
+    out->abi_version = DICEGP_ABI_VERSION;
+    out->sm_count = ctx ? ctx->sm_count : 0;
+    return DICEGP_OK;
+}
+
+int dicegp_upload_genes(dicegp_ctx *c, int32_t G, int32_t T, const int32_t *n_iso, const int32_t *n_reads,
+                        const double *W, int64_t w_count, const double *len_iso, int64_t len_count) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (G <= 0 || T <= 0 || !n_iso || !n_reads || !len_iso || (w_count > 0 && !W))
+        return c->fail(DICEGP_ERR_ARG, "upload_genes: NULL or non-positive argument");
+    if (T > DG_MAXT) return c->fail(DICEGP_ERR_LIMIT, "upload_genes: T beyond max_times");
+    DG_CUDA(c, cudaSetDevice(c->device));
+    c->G = 0; c->n_chains = 0;
+    c->hC.assign(n_iso, n_iso + G);
+    c->hncnt.assign(n_reads, n_reads + (size_t)G * T);
+    c->hroff.assign((size_t)G * (T + 1), 0);
+    c->hwoff.assign(G, 0);
+    c->hlenoff.assign(G, 0);
+    int64_t w = 0, l = 0;
+    for (int g = 0; g < G; ++g) {
+        const int C = n_iso[g];
+        if (C < 1 || C > DG_MAXC) return c->fail(DICEGP_ERR_LIMIT, "upload_genes: isoform count outside [1, max_isoforms]");
+        if ((int64_t)C * T > DG_MAXCT) return c->fail(DICEGP_ERR_LIMIT, "upload_genes: C*T beyond the compiled limit");
+        c->hwoff[g] = w; c->hlenoff[g] = l;
+        int64_t r = 0;
+        for (int t = 0; t < T; ++t) {
+            const int n = n_reads[(size_t)g * T + t];
+            if (n < 0) return c->fail(DICEGP_ERR_ARG, "upload_genes: negative read count");
+            c->hroff[(size_t)g * (T + 1) + t] = (int32_t)r;
+            r += n + (n & 1);
+            if (r > 0x7fffffff) return c->fail(DICEGP_ERR_LIMIT, "upload_genes: more than 2^31 reads in one gene");
+        }
+        c->hroff[(size_t)g * (T + 1) + T] = (int32_t)r;
+        w += (int64_t)C * r;
+        l += (int64_t)C * T;
+    }
+    if (w != w_count) return c->fail(DICEGP_ERR_ARG, "upload_genes: w_count does not match the packed layout");
+    if (l != len_count) return c->fail(DICEGP_ERR_ARG, "upload_genes: len_count does not match sum C*T");
+    if (c->dC.resize(G) != cudaSuccess || c->dncnt.resize((size_t)G * T) != cudaSuccess ||
+        c->droff.resize((size_t)G * (T + 1)) != cudaSuccess || c->dwoff.resize(G) != cudaSuccess ||
+        c->dlenoff.resize(G) != cudaSuccess || c->dW.resize(std::max<int64_t>(w, 2)) != cudaSuccess ||
+        c->dlen.resize(l) != cudaSuccess)
+        return c->fail(DICEGP_ERR_NOMEM, "upload_genes: device allocation failed");
+    DG_CUDA(c, cudaMemcpyAsync(c->dC.p, c->hC.data(), G * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    DG_CUDA(c, cudaMemcpyAsync(c->dncnt.p, c->hncnt.data(), (size_t)G * T * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    DG_CUDA(c, cudaMemcpyAsync(c->droff.p, c->hroff.data(), (size_t)G * (T + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    DG_CUDA(c, cudaMemcpyAsync(c->dwoff.p, c->hwoff.data(), G * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    DG_CUDA(c, cudaMemcpyAsync(c->dlenoff.p, c->hlenoff.data(), G * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (w > 0) DG_CUDA(c, cudaMemcpyAsync(c->dW.p, W, w * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    DG_CUDA(c, cudaMemcpyAsync(c->dlen.p, len_iso, l * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    DG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->G = G; c->T = T;
+    return DICEGP_OK;
+}
+
+static int install_chains(dicegp_ctx *c, int32_t n, const dicegp_chain_desc *desc, const double *pool,
+                          int64_t pool_count, bool pool_on_device) {
+    c->n_chains = 0;
+    c->hdesc.assign(desc, desc + n);
+    c->htrace_off.assign(n, 0);
+    c->hst_off.assign(n, 0);
+    std::vector<int32_t> gene(n), t0(n), Tc(n), M(n), ini(n), gap(n);
+    std::vector<int64_t> kinv(n), pf(n), js(n), jc(n), y0(n);
+    std::vector<double> prior(n);
+    int64_t tr = 0, st = 0;
+    for (int i = 0; i < n; ++i) {
+        const dicegp_chain_desc &d = desc[i];
+        if (d.gene < 0 || d.gene >= c->G) return c->fail(DICEGP_ERR_ARG, "set_chains: gene index out of range");
+        if (d.Tc < 1 || d.t0 < 0 || d.t0 + d.Tc > c->T) return c->fail(DICEGP_ERR_ARG, "set_chains: time range outside the gene");
+        if (d.M < 1 || d.gap < 1 || d.initial < 0) return c->fail(DICEGP_ERR_ARG, "set_chains: M/initial/gap invalid");
+        const int C = c->hC[d.gene];
+        const int64_t need[4] = {d.kinv_off + (int64_t)d.Tc * d.Tc, d.jump_scale_off + C - 1, d.jump_const_off + C - 1,
+                                 d.y0_off >= 0 ? d.y0_off + (int64_t)C * d.Tc : 0};
+        if (d.kinv_off < 0 || d.jump_scale_off < 0 || d.jump_const_off < 0) return c->fail(DICEGP_ERR_ARG, "set_chains: negative pool offset");
+        for (int k = 0; k < 4; ++k)
+            if (need[k] > pool_count) return c->fail(DICEGP_ERR_ARG, "set_chains: pool offset beyond pool_count");
+        if (d.prop_factor_off >= 0 && d.prop_factor_off + (int64_t)d.Tc * d.Tc > pool_count)
+            return c->fail(DICEGP_ERR_ARG, "set_chains: prop_factor offset beyond pool_count");
+        gene[i] = d.gene; t0[i] = d.t0; Tc[i] = d.Tc; M[i] = d.M; ini[i] = d.initial; gap[i] = d.gap;
+        kinv[i] = d.kinv_off; pf[i] = d.prop_factor_off; js[i] = d.jump_scale_off; jc[i] = d.jump_const_off;
+        y0[i] = d.y0_off; prior[i] = d.prior_const;
+        c->htrace_off[i] = tr; c->hst_off[i] = st;
+        const int64_t rowlen = 2 * (int64_t)C * d.Tc + 2;
+        tr += rowlen * d.M;
+        st += rowlen;
+    }
+#define DG_RESIZE(buf, cnt) if ((buf).resize(cnt) != cudaSuccess) return c->fail(DICEGP_ERR_NOMEM, "set_chains: device allocation failed (" #buf ")")
+    DG_RESIZE(c->cgene, n); DG_RESIZE(c->ct0, n); DG_RESIZE(c->cTc, n); DG_RESIZE(c->cM, n);
+    DG_RESIZE(c->cinit, n); DG_RESIZE(c->cgap, n); DG_RESIZE(c->cm_next, n); DG_RESIZE(c->ccnt, n);
+    DG_RESIZE(c->cstate, n); DG_RESIZE(c->cm_ret, n); DG_RESIZE(c->cflags, n);
+    DG_RESIZE(c->ckinv, n); DG_RESIZE(c->cpf, n); DG_RESIZE(c->cjs, n); DG_RESIZE(c->cjc, n);
+    DG_RESIZE(c->cy0, n); DG_RESIZE(c->ctrace_off, n); DG_RESIZE(c->cst_off, n); DG_RESIZE(c->cstream_id, n);
+    DG_RESIZE(c->cprior, n); DG_RESIZE(c->cst, st);
+    if (!pool_on_device) DG_RESIZE(c->cpool, std::max<int64_t>(pool_count, 1));
+    if (c->ctrace.resize(tr) != cudaSuccess) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "set_chains: cannot allocate %.1f GB of trace memory; use fewer chains per batch", tr * 8.0 / 1e9);
+        return c->fail(DICEGP_ERR_NOMEM, msg);
+    }
+#undef DG_RESIZE
+    cudaStream_t s = c->stream;
+#define DG_UP(dst, src, type) DG_CUDA(c, cudaMemcpyAsync((dst).p, (src).data(), n * sizeof(type), cudaMemcpyHostToDevice, s))
+    DG_UP(c->cgene, gene, int32_t); DG_UP(c->ct0, t0, int32_t); DG_UP(c->cTc, Tc, int32_t); DG_UP(c->cM, M, int32_t);
+    DG_UP(c->cinit, ini, int32_t); DG_UP(c->cgap, gap, int32_t);
+    DG_UP(c->ckinv, kinv, int64_t); DG_UP(c->cpf, pf, int64_t); DG_UP(c->cjs, js, int64_t); DG_UP(c->cjc, jc, int64_t);
+    DG_UP(c->cy0, y0, int64_t); DG_UP(c->ctrace_off, c->htrace_off, int64_t); DG_UP(c->cst_off, c->hst_off, int64_t);
+    DG_UP(c->cprior, prior, double);
+#undef DG_UP
+    if (!pool_on_device && pool_count > 0)
+        DG_CUDA(c, cudaMemcpyAsync(c->cpool.p, pool, pool_count * sizeof(double), cudaMemcpyHostToDevice, s));
+    DG_CUDA(c, cudaMemsetAsync(c->cm_next.p, 0, n * sizeof(int32_t), s));
+    DG_CUDA(c, cudaMemsetAsync(c->ccnt.p, 0, n * sizeof(int32_t), s));
+    DG_CUDA(c, cudaMemsetAsync(c->cstate.p, 0, n * sizeof(int32_t), s));
+    DG_CUDA(c, cudaMemsetAsync(c->cm_ret.p, 0, n * sizeof(int32_t), s));
+    DG_CUDA(c, cudaMemsetAsync(c->cflags.p, 0, n * sizeof(int32_t), s));
+    DG_CUDA(c, cudaStreamSynchronize(s));
+    c->have_stream_id = false;
+    c->n_chains = n;
+    return DICEGP_OK;
+}
+
+int dicegp_set_chains(dicegp_ctx *c, int32_t n, const dicegp_chain_desc *desc, const double *pool,
+                      int64_t pool_count) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (c->G == 0) return c->fail(DICEGP_ERR_STATE, "set_chains: upload genes first");
+    if (n <= 0 || !desc || (pool_count > 0 && !pool)) return c->fail(DICEGP_ERR_ARG, "set_chains: NULL or empty argument");
+    DG_CUDA(c, cudaSetDevice(c->device));
+    return install_chains(c, n, desc, pool, pool_count, false);
+}
+
+int dicegp_main_chains_from_prerun(dicegp_ctx *c, int32_t M, int32_t initial, int32_t gap, double theta1,
+                                   const double *kinv, const double *prop_factor, double prior_const,
+                                   double *var_out) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (c->G == 0 || c->n_chains != c->G * c->T)
+        return c->fail(DICEGP_ERR_STATE, "main_chains_from_prerun: expects G*T finished pre-run chains");
+    if (!kinv) return c->fail(DICEGP_ERR_ARG, "main_chains_from_prerun: kinv is NULL");
+    DG_CUDA(c, cudaSetDevice(c->device));
+    const int G = c->G, T = c->T;
+    for (int i = 0; i < c->n_chains; ++i) {
+        const dicegp_chain_desc &d = c->hdesc[i];
+        if (d.gene != i / T || d.t0 != i % T || d.Tc != 1)
+            return c->fail(DICEGP_ERR_STATE, "main_chains_from_prerun: chain g*T+j must be the pre-run of gene g, time j");
+    }
+    std::vector<int32_t> st(c->n_chains);
+    DG_CUDA(c, cudaMemcpy(st.data(), c->cstate.p, c->n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int32_t s : st)
+        if (s == 0) return c->fail(DICEGP_ERR_STATE, "main_chains_from_prerun: a pre-run chain has not finished");
+    DG_CUDA(c, c->dvar.resize((size_t)G * DG_MAXC));
+    {
+        const int threads = 128, total = G * DG_MAXC;
+        dicegp_prerun_var_kernel<<<(total + threads - 1) / threads, threads, 0, c->stream>>>(
+            make_gene_tab(c), make_chain_tab(c), G, c->dvar.p);
+        DG_CUDA(c, cudaGetLastError());
+    }
+    std::vector<double> var((size_t)G * DG_MAXC);
+    DG_CUDA(c, cudaMemcpyAsync(var.data(), c->dvar.p, var.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    DG_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (var_out) memcpy(var_out, var.data(), var.size() * sizeof(double));
+    // new chain set: pool = [kinv TT][pfac TT] + per gene [js C-1][jc C-1]
+    const int TT = T * T;
+    std::vector<double> pool(2 * (size_t)TT);
+    memcpy(pool.data(), kinv, TT * sizeof(double));
+    if (prop_factor) memcpy(pool.data() + TT, prop_factor, TT * sizeof(double));
+    std::vector<dicegp_chain_desc> desc(G);
+    for (int g = 0; g < G; ++g) {
+        const int C = c->hC[g];
+        dicegp_chain_desc &d = desc[g];
+        d.gene = g; d.t0 = 0; d.Tc = T; d.M = M; d.initial = initial; d.gap = gap;
+        d.kinv_off = 0; d.prop_factor_off = prop_factor ? TT : -1; d.y0_off = -1;
+        d.prior_const = prior_const;
+        d.jump_scale_off = (int64_t)pool.size();
+        for (int k = 0; k < C - 1; ++k) pool.push_back(var[(size_t)g * DG_MAXC + k] * 5 / ((double)(T * C) * theta1));
+        d.jump_const_off = (int64_t)pool.size();
+        for (int k = 0; k < C - 1; ++k) {
+            const double js = pool[d.jump_scale_off + k];
+            pool.push_back(prior_const - (double)T * std::log(js) / 2.0);
+        }
+    }
+    return install_chains(c, G, desc.data(), pool.data(), (int64_t)pool.size(), false);
+}
+
+int dicegp_run_host_stream(dicegp_ctx *c, int32_t n, const int32_t *chain_ids, int32_t n_steps,
+                           const double *delta, const int64_t *delta_off, int64_t delta_count,
+                           const double *u) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (c->n_chains == 0) return c->fail(DICEGP_ERR_STATE, "run_host_stream: no chains");
+    if (n <= 0 || n_steps <= 0 || !chain_ids || !delta_off || !u || (delta_count > 0 && !delta))
+        return c->fail(DICEGP_ERR_ARG, "run_host_stream: NULL or non-positive argument");
+    DG_CUDA(c, cudaSetDevice(c->device));
+    std::vector<int32_t> ids(chain_ids, chain_ids + n);
+    std::vector<int64_t> doff(delta_off, delta_off + n);
+    std::vector<char> seen(c->n_chains, 0);
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || ids[i] >= c->n_chains) return c->fail(DICEGP_ERR_ARG, "run_host_stream: chain id out of range");
+        if (seen[ids[i]]) return c->fail(DICEGP_ERR_ARG, "run_host_stream: chain listed twice");
+        seen[ids[i]] = 1;
+        const dicegp_chain_desc &d = c->hdesc[ids[i]];
+        const int64_t need = (int64_t)n_steps * (c->hC[d.gene] - 1) * d.Tc;
+        if (doff[i] < 0 || doff[i] + need > delta_count) return c->fail(DICEGP_ERR_ARG, "run_host_stream: delta block outside delta_count");
+    }
+    DG_CUDA(c, c->ddelta.resize(std::max<int64_t>(delta_count, 1)));
+    DG_CUDA(c, c->du.resize((size_t)n * n_steps));
+    if (delta_count > 0)
+        DG_CUDA(c, cudaMemcpyAsync(c->ddelta.p, delta, delta_count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    DG_CUDA(c, cudaMemcpyAsync(c->du.p, u, (size_t)n * n_steps * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    StreamArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.mode = 0;
+    sa.delta = c->ddelta.p;
+    sa.u = c->du.p;
+    return run_chains(c, ids, n_steps, sa, &doff, false);
+}
+
+int dicegp_run_device_stream(dicegp_ctx *c, uint64_t seed, const int64_t *stream_id) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (c->n_chains == 0) return c->fail(DICEGP_ERR_STATE, "run_device_stream: no chains");
+    DG_CUDA(c, cudaSetDevice(c->device));
+    for (int i = 0; i < c->n_chains; ++i)
+        if (c->hdesc[i].prop_factor_off < 0)
+            return c->fail(DICEGP_ERR_ARG, "run_device_stream: chain without prop_factor");
+    if (stream_id) {
+        DG_CUDA(c, cudaMemcpyAsync(c->cstream_id.p, stream_id, c->n_chains * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        c->have_stream_id = true;
+    } else {
+        c->have_stream_id = false;
+    }
+    std::vector<int32_t> ids(c->n_chains);
+    int max_M = 0;
+    for (int i = 0; i < c->n_chains; ++i) { ids[i] = i; max_M = std::max(max_M, c->hdesc[i].M); }
+    StreamArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.mode = 1;
+    sa.seed = seed;
+    return run_chains(c, ids, max_M, sa, nullptr, true);
+}
+
+int dicegp_chain_status(dicegp_ctx *c, int32_t n, const int32_t *chain_ids, int32_t *m_ret, int32_t *n_rows,
+                        int32_t *cnt, int32_t *state, int32_t *flags) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (c->n_chains == 0) return c->fail(DICEGP_ERR_STATE, "chain_status: no chains");
+    if (n <= 0 || !chain_ids) return c->fail(DICEGP_ERR_ARG, "chain_status: NULL or empty id list");
+    DG_CUDA(c, cudaSetDevice(c->device));
+    const int N = c->n_chains;
+    std::vector<int32_t> a(N), b(N), s(N), f(N), mn(N);
+    DG_CUDA(c, cudaMemcpy(a.data(), c->cm_ret.p, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    DG_CUDA(c, cudaMemcpy(b.data(), c->ccnt.p, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    DG_CUDA(c, cudaMemcpy(s.data(), c->cstate.p, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    DG_CUDA(c, cudaMemcpy(f.data(), c->cflags.p, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    DG_CUDA(c, cudaMemcpy(mn.data(), c->cm_next.p, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        const int id = chain_ids[i];
+        if (id < 0 || id >= N) return c->fail(DICEGP_ERR_ARG, "chain_status: chain id out of range");
+        if (m_ret) m_ret[i] = a[id];
+        if (cnt) cnt[i] = b[id];
+        if (state) state[i] = s[id];
+        if (flags) flags[i] = f[id];
+        if (n_rows) n_rows[i] = s[id] == DICEGP_CHAIN_CONVERGED ? a[id] : (s[id] == DICEGP_CHAIN_EXHAUSTED ? c->hdesc[id].M : mn[id]);
+    }
+    return DICEGP_OK;
+}
+
+int dicegp_download_trace(dicegp_ctx *c, int32_t chain, int32_t first_row, int32_t n_rows, double *psi,
+                          double *y, double *pro, double *lik) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (chain < 0 || chain >= c->n_chains) return c->fail(DICEGP_ERR_ARG, "download_trace: chain id out of range");
+    const dicegp_chain_desc &d = c->hdesc[chain];
+    if (first_row < 0 || n_rows < 0 || first_row + n_rows > d.M) return c->fail(DICEGP_ERR_ARG, "download_trace: row range outside the trace");
+    if (n_rows == 0) return DICEGP_OK;
+    DG_CUDA(c, cudaSetDevice(c->device));
+    const int CT = c->hC[d.gene] * d.Tc;
+    const size_t rowlen = 2 * (size_t)CT + 2;
+    const double *src = c->ctrace.p + c->htrace_off[chain] + (size_t)first_row * rowlen;
+    const size_t pitch = rowlen * sizeof(double);
+    if (psi) DG_CUDA(c, cudaMemcpy2D(psi, CT * sizeof(double), src, pitch, CT * sizeof(double), n_rows, cudaMemcpyDeviceToHost));
+    if (y) DG_CUDA(c, cudaMemcpy2D(y, CT * sizeof(double), src + CT, pitch, CT * sizeof(double), n_rows, cudaMemcpyDeviceToHost));
+    if (pro) DG_CUDA(c, cudaMemcpy2D(pro, sizeof(double), src + 2 * CT, pitch, sizeof(double), n_rows, cudaMemcpyDeviceToHost));
+    if (lik) DG_CUDA(c, cudaMemcpy2D(lik, sizeof(double), src + 2 * CT + 1, pitch, sizeof(double), n_rows, cudaMemcpyDeviceToHost));
+    return DICEGP_OK;
+}
+
+int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids, double *psi_mean, double *psi_ci,
+                             const int64_t *out_off, double *lik_marg) {
+    (void)n; (void)chain_ids; (void)psi_mean; (void)psi_ci; (void)out_off; (void)lik_marg;
+    if (!c) return DICEGP_ERR_ARG;
+    return c->fail(DICEGP_ERR_STATE, "posterior_summary: not built yet (SURVEY.md 8(f)#1); download the trace");
+}
+
+int dicegp_last_run_stats(dicegp_ctx *c, double *kernel_ms, int64_t *launches, int64_t *read_evals, int64_t *steps) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (kernel_ms) *kernel_ms = c->last_ms;
+    if (launches) *launches = c->last_launches;
+    if (read_evals) *read_evals = c->last_evals;
+    if (steps) *steps = c->last_steps;
+    return DICEGP_OK;
+}
+
+}  // extern "C"
