@@ -12,8 +12,8 @@ namespace dg {
 // ---------------------------------------------------------------------------------------
 template <int KC, bool LOGPATH>
 __device__ __forceinline__ void lik_partial(const double *__restrict__ Wc, int C, int Tc,
-                                            const int *__restrict__ rel, const int *__restrict__ ncnt,
-                                            const double *__restrict__ fsi, int tid, int nthreads,
+                                            const int *rel, const int *ncnt,
+                                            const double *fsi, int tid, int nthreads,
                                             MantExp &acc, double &logsum) {
     constexpr int KR = KC > 0 ? KC : 1;
     int it = 0;
@@ -126,7 +126,7 @@ __device__ __forceinline__ void evaluate(ChainCtx &s, bool with_q) {
         }
         const double sg = dg_np_sum(s.fsi + t, C, Tc);
         for (int k = 0; k < C; ++k) s.fsi[k * Tc + t] = s.fsi[k * Tc + t] / sg;
-    } else if (tid == 32 || (s.nthreads <= 32 && tid == 0)) {
+    } else if (tid == 32) {
         // warp 1 (idle in phase 3 when Tc <= 32): prior and proposal density, c ascending
         double prior = 0.0, Q = 0.0;
         for (int c = 0; c < C - 1; ++c) {
@@ -196,8 +196,9 @@ __device__ __forceinline__ void evaluate(ChainCtx &s, bool with_q) {
 // Two-pass mean / population variance like np.mean / np.var.  Lanes walk columns
 // (coalesced), warps walk rows.  Returns 1 to every thread when all |Z| <= 2.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ int geweke_converged(ChainCtx &s, const double *__restrict__ trace,
-                                                int rowlen, int m) {
+// The trace is written by this very kernel: read it with ld.global.cg (L2), never through
+// the non-coherent path.
+__device__ __forceinline__ int geweke_converged(ChainCtx &s, const double *trace, int rowlen, int m) {
     const int nA = (int)(0.1 * (double)m);
     const int iB = (int)(0.5 * (double)m);
     const int nB = m - iB;
@@ -209,8 +210,8 @@ __device__ __forceinline__ int geweke_converged(ChainCtx &s, const double *__res
         // pass 1: sums
         double sa = 0.0, sb = 0.0;
         if (act) {
-            for (int r = s.warp; r < nA; r += s.nwarps) sa += trace[(size_t)r * rowlen + col];
-            for (int r = iB + s.warp; r < m; r += s.nwarps) sb += trace[(size_t)r * rowlen + col];
+            for (int r = s.warp; r < nA; r += s.nwarps) sa += __ldcg(trace + (size_t)r * rowlen + col);
+            for (int r = iB + s.warp; r < m; r += s.nwarps) sb += __ldcg(trace + (size_t)r * rowlen + col);
         }
         gA[s.warp * DG_GW_COLS + s.lane] = sa;
         gB[s.warp * DG_GW_COLS + s.lane] = sb;
@@ -227,11 +228,11 @@ __device__ __forceinline__ int geweke_converged(ChainCtx &s, const double *__res
         double qa = 0.0, qb = 0.0;
         if (act) {
             for (int r = s.warp; r < nA; r += s.nwarps) {
-                double d = trace[(size_t)r * rowlen + col] - meanA;
+                double d = __ldcg(trace + (size_t)r * rowlen + col) - meanA;
                 qa = fma(d, d, qa);
             }
             for (int r = iB + s.warp; r < m; r += s.nwarps) {
-                double d = trace[(size_t)r * rowlen + col] - meanB;
+                double d = __ldcg(trace + (size_t)r * rowlen + col) - meanB;
                 qb = fma(d, d, qb);
             }
         }
@@ -484,6 +485,8 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         ct.flags[chain] = flags;
         ct.m_ret[chain] = m_ret;
         ct.state[chain] = state;
+        if (W_IN_SMEM && use_tma)
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(dg_smem_u32(mbar)) : "memory");
     }
     __syncthreads();
 }

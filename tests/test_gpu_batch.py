@@ -1,0 +1,104 @@
+"""Batched pipeline on the GPU: device-generated streams, properties that hold at any size."""
+import numpy as np
+import pytest
+
+from diceseq_b200 import synth
+from diceseq_b200.batch import BatchSampler
+from diceseq_b200.packer import pack_genes
+from oracle import psi_gp_mh_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(config, genes, **kw):
+    return pack_genes([synth.gene_W(config, g, **kw) for g in genes])
+
+
+def _loglik_numpy(W_list, lens, Y):
+    """sum_t sum_n log(W_t f_t) recomputed on the host from a trace row."""
+    tot = 0.0
+    for t, W in enumerate(W_list):
+        e = np.exp(Y[:, t])
+        psi = e / e.sum()
+        f = lens[t] * psi
+        f = f / f.sum()
+        tot += np.log(W @ f).sum()
+    return tot
+
+
+@pytest.fixture(scope="module")
+def sampler():
+    s = BatchSampler(0)
+    yield s
+    s.close()
+
+
+def test_trace_rows_are_self_consistent_full_size(sampler):
+    """Size-independent property at BASELINE shapes (1000 reads x 8 time points, C in 2..8):
+    every stored Lik_all[m] equals the likelihood of the stored Y_all[m], psi = softmax(y),
+    Pro - Lik = GP prior of y, and the Geweke rule holds at the returned m."""
+    genes = list(range(40, 52))
+    packed = _batch("timeseries", genes)
+    res = sampler.run(packed, M=3000, initial=1000, gap=100, seed=5, gene_ids=genes, keep_trace=True)
+    T = 8
+    X = np.arange(T)
+    K = orc.gp_kernel(X, [3.0, synth.default_theta2(X)])
+    for g, r in zip(genes, res):
+        W_list, lens = synth.gene_W("timeseries", g)
+        Psi, Y, Pro, Lik = r.trace
+        assert Psi.shape[0] == (r.m if r.state == 1 else 3000)
+        for row in (0, len(Lik) // 2, len(Lik) - 1):
+            ll = _loglik_numpy(W_list, lens, Y[row])
+            assert abs(ll - Lik[row]) <= 1e-12 * abs(ll)
+            e = np.exp(Y[row])
+            assert np.allclose(Psi[row], e / e.sum(axis=0), rtol=1e-13, atol=0)
+            prior = sum(orc.log_mvn_pdf(Y[row, c], np.zeros(T), K) for c in range(Y.shape[1] - 1))
+            assert abs((Pro[row] - Lik[row]) - prior) <= 1e-9 * max(1.0, abs(prior))
+        assert (Y[:, -1, :] == 0).all()
+        if r.state == 1:
+            for c in range(Psi.shape[1] - 1):
+                for t in range(T):
+                    z = orc.geweke_z(Psi[:r.m, c, t])
+                    assert z is not None and z <= 2
+        assert 0 < r.cnt <= len(Lik)
+
+
+def test_device_stream_is_deterministic_and_partition_invariant(sampler):
+    genes = [60, 61, 62, 63, 64, 65]
+    a = sampler.run(_batch("static", genes), M=1500, seed=9, gene_ids=genes, keep_trace=True)
+    b = sampler.run(_batch("static", genes[3:]), M=1500, seed=9, gene_ids=genes[3:], keep_trace=True)
+    for ra, rb in zip(a[3:], b):
+        assert ra.m == rb.m and ra.cnt == rb.cnt
+        assert np.array_equal(ra.trace[2], rb.trace[2])
+    c = sampler.run(_batch("static", genes), M=1500, seed=10, gene_ids=genes, keep_trace=True)
+    assert any(not np.array_equal(x.trace[2][:50], y.trace[2][:50]) for x, y in zip(a, c))
+
+
+def test_posterior_matches_oracle_within_mc_error(sampler):
+    """Independent streams: posterior mean psi of the GPU chain vs the oracle's (MT19937)
+    on the same genes.  Tolerance 0.05 absolute on psi (CI half-widths are 0.05-0.1)."""
+    genes = [70, 71, 72, 73]
+    packed = _batch("timeseries", genes, reads=200, T=3)
+    res = sampler.run(packed, M=4000, initial=1000, gap=100, seed=3, gene_ids=genes)
+    X = np.arange(3)
+    for g, r in zip(genes, res):
+        R, L, P = synth.gene_matrices("timeseries", g, reads=200, T=3)
+        with np.errstate(all="ignore"):
+            out, var, _ = orc.prerun_and_main(R, L, P, X, 3.0, float(synth.default_theta2(X)), 4000, 1000, 100,
+                                              rng=np.random.RandomState(g))
+        Psi, Y, th2, Pro, Lik, cnt, m = out
+        ref_mean = Psi[int(m / 4):].mean(axis=0)
+        assert np.abs(ref_mean - r.psi_mean).max() < 0.05, (g, ref_mean, r.psi_mean)
+        assert 0.2 < r.var.mean() / var.mean() < 5.0
+
+
+def test_host_stream_batch_runs_and_is_consistent(sampler):
+    genes = [80, 81, 82]
+    packed = _batch("timeseries", genes, reads=150, T=4)
+    res = sampler.run(packed, M=2000, initial=1000, gap=100, seed=4, gene_ids=genes, stream="host", keep_trace=True)
+    for g, r in zip(genes, res):
+        W_list, lens = synth.gene_W("timeseries", g, reads=150, T=4)
+        Psi, Y, Pro, Lik = r.trace
+        ll = _loglik_numpy(W_list, lens, Y[-1])
+        assert abs(ll - Lik[-1]) <= 1e-12 * abs(ll)
+        assert r.state in (1, 2) and r.cnt > 0

@@ -1,0 +1,95 @@
+"""Host-side logic of the product path (CPU only): cleaning, packing, helpers, chunking."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from diceseq_b200 import GP_K, Geweke_Z, normal_pdf, synth
+from diceseq_b200.model_GP import ChainConstants, check_steps, legacy_stream_chunk
+from diceseq_b200.packer import clean_inputs, pack_genes
+from oracle import psi_gp_mh_oracle as orc
+
+
+def test_helpers_match_oracle():
+    X = np.array([1.5, 2.5, 5.0])
+    th = [3.0, 1.44]
+    assert np.array_equal(GP_K(X, th), orc.gp_kernel(X, th))
+    K = GP_K(X, th)
+    x = np.array([0.3, -0.2, 0.9])
+    assert normal_pdf(x, np.zeros(3), K) == orc.log_mvn_pdf(x, np.zeros(3), K)
+    assert normal_pdf(x, np.zeros(3), -K) is None
+    tr = np.random.RandomState(0).rand(1000)
+    assert Geweke_Z(tr) == orc.geweke_z(tr)
+    assert Geweke_Z(np.ones(100)) is None
+    # N-point and scalar-mean forms
+    pts = np.random.RandomState(1).randn(5, 3)
+    out = normal_pdf(pts, np.zeros(3), K)
+    assert out.shape == (5,) and np.isclose(out[0], orc.log_mvn_pdf(pts[0], np.zeros(3), K))
+
+
+def test_cleaning_matches_oracle():
+    R, L, P, _kw, _z = load_golden("edge_nan")
+    R2, L2, P2 = [r.copy() for r in R], [l.copy() for l in L], [p.copy() for p in P]
+    clean_inputs(R, L, P)
+    orc.clean_inputs(R2, L2, P2)
+    for t in range(len(R)):
+        assert np.array_equal(R[t], R2[t]) and np.array_equal(L[t], L2[t]) and np.array_equal(P[t], P2[t])
+
+
+def test_pack_layout():
+    W0 = np.arange(15, dtype=float).reshape(5, 3) + 1     # odd read count -> one pad column
+    W1 = np.zeros((0, 3))
+    lens = [np.array([1.0, 2.0, 3.0]), np.array([4.0, 5.0, 6.0])]
+    Wb = np.arange(8, dtype=float).reshape(4, 2) + 100
+    p = pack_genes([([W0, W1], lens), ([Wb, Wb[:2]], [np.ones(2), 2 * np.ones(2)])])
+    assert p.G == 2 and p.T == 2
+    assert list(p.n_iso) == [3, 2] and list(p.n_reads) == [5, 0, 4, 2]
+    blk = p.W[:18].reshape(3, 6)
+    assert np.array_equal(blk[:, :5], W0.T) and (blk[:, 5] == 0).all()
+    assert np.array_equal(p.W[18:26].reshape(2, 4), Wb.T)
+    assert np.array_equal(p.W[26:30].reshape(2, 2), Wb[:2].T)
+    assert p.W.size == 30
+    assert np.array_equal(p.len_iso, [1, 2, 3, 4, 5, 6, 1, 1, 2, 2])
+    sub = p.subset([1])
+    assert sub.G == 1 and np.array_equal(sub.W, p.W[18:]) and np.array_equal(sub.len_iso, [1, 1, 2, 2])
+
+
+def test_check_steps():
+    assert check_steps(20000, 1000, 100)[:3] == [1001, 1101, 1201]
+    assert check_steps(20000, 1000, 100)[-1] == 20000
+    assert check_steps(100, 100, 50) == [100]
+    assert check_steps(300, 100, 50) == [101, 151, 201, 251, 300]
+    assert check_steps(1500, 950, 100) == [1001, 1101, 1201, 1301, 1401, 1500]
+    assert check_steps(1001, 1000, 100) == [1001]
+
+
+def test_stream_replays_reference_rng():
+    """The wrapper's stream generator consumes numpy's legacy state in the reference's
+    interleaving: its increments equal what the oracle records under the same seed."""
+    R, L, P, kw, z = load_golden("joint_t3_c2")
+    rec = orc.StepRecord()
+    orc.psi_gp_mh(R, L, P, record=rec, **kw)
+    delta_ref, u_ref = rec.arrays()[:2]
+    C, T = 2, 3
+    consts = ChainConstants(kw["X"], C, 0.05 * np.ones(C - 1), kw["theta1"], kw["theta2"])
+    np.random.seed(kw["randomS"])
+    delta, u = legacy_stream_chunk(len(u_ref), consts.factors, T)
+    assert np.array_equal(delta[:, 0, :], delta_ref) and np.array_equal(u, u_ref)
+
+
+def test_synth_is_seeded_and_shaped():
+    a = synth.gene_matrices("timeseries", 5)
+    b = synth.gene_matrices("timeseries", 5)
+    assert len(a[0]) == 8 and a[0][0].shape[0] == 1000 and 2 <= a[0][0].shape[1] <= 8
+    assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a[2], b[2]))
+    R, L, P = synth.gene_matrices("static", 1)
+    assert len(R) == 1 and R[0].shape == (1000, 3)
+    assert np.isnan(P[0][~R[0]]).all() and (P[0][R[0]] > 0).all()
+    W, lens = synth.gene_W("static", 1)
+    assert (W[0].sum(axis=1) > 0).all()
+
+
+def test_theta2_none_is_refused_not_faked():
+    from diceseq_b200 import Psi_GP_MH
+    R, L, P, kw, _z = load_golden("learn_c2")
+    with pytest.raises(NotImplementedError):
+        Psi_GP_MH(R, L, P, **kw)
