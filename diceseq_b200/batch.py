@@ -105,7 +105,7 @@ class BatchSampler:
                     offs.append(o)
                     o += d.size
                 delta = np.concatenate(blocks) if blocks else np.zeros(0)
-                u = rng.random_sample((active.size, S))
+                u = rng.random((active.size, S))
                 ctx.run_host_stream(active, S, delta, offs, u.ravel())
                 self._acc_stats()
                 start += S

@@ -49,25 +49,51 @@ dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__res
 
 // numpy pairwise sum (n <= 128) over a strided global series, used where the reference
 // reduces a 1-D view (np.var of a (rows,1) slice collapses to 1-D and goes pairwise).
-__device__ double dg_pw_global(const double *v, int n, size_t stride) {
+__device__ double dg_pw_block(const double *v, int n, size_t stride) {
     if (n < 8) {
         double r = 0.0;
         for (int i = 0; i < n; ++i) r += v[i * stride];
         return r;
     }
-    if (n <= 128) {
-        double r[8];
-        for (int j = 0; j < 8; ++j) r[j] = v[j * stride];
-        int i = 8;
-        for (; i < n - (n % 8); i += 8)
-            for (int j = 0; j < 8; ++j) r[j] += v[(i + j) * stride];
-        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += v[i * stride];
-        return res;
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = v[j * stride];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] += v[(i + j) * stride];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += v[i * stride];
+    return res;
+}
+// numpy splits n > 128 recursively (n2 = n/2 rounded down to a multiple of 8); walked here
+// with an explicit stack because device recursion needs a run-time stack size.
+__device__ double dg_pw_global(const double *v, int n, size_t stride) {
+    if (n <= 128) return dg_pw_block(v, n, stride);
+    int f_off[32], f_n[32], f_state[32], fs = 0, rs = 0;
+    double res[34];
+    f_off[0] = 0; f_n[0] = n; f_state[0] = 0; fs = 1;
+    while (fs > 0) {
+        const int k = fs - 1;
+        if (f_n[k] <= 128) {
+            res[rs++] = dg_pw_block(v + (size_t)f_off[k] * stride, f_n[k], stride);
+            --fs;
+            continue;
+        }
+        int n2 = f_n[k] / 2;
+        n2 -= n2 % 8;
+        if (f_state[k] == 0) {
+            f_state[k] = 1;
+            f_off[fs] = f_off[k]; f_n[fs] = n2; f_state[fs] = 0; ++fs;
+        } else if (f_state[k] == 1) {
+            f_state[k] = 2;
+            f_off[fs] = f_off[k] + n2; f_n[fs] = f_n[k] - n2; f_state[fs] = 0; ++fs;
+        } else {
+            const double r = res[rs - 1], l = res[rs - 2];
+            rs -= 2;
+            res[rs++] = l + r;
+            --fs;
+        }
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return dg_pw_global(v, n2, stride) + dg_pw_global(v + n2 * stride, n - n2, stride);
+    return res[0];
 }
 
 // Jump variance from the pre-runs (run_utils.py:111-116).  One thread per (gene, isoform):
@@ -150,6 +176,7 @@ struct dicegp_ctx {
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
+    size_t static_smem = 0;      // static shared memory of the chain kernel
     std::string err;
     cudaStream_t stream = nullptr;
     cudaStream_t class_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -226,7 +253,7 @@ void launch_classes(const dicegp_ctx *c, LaunchClass out[5]) {
     const int thr[4] = {128, 256, 512, 1024};
     for (int i = 0; i < 4; ++i) {
         size_t lim = per_sm / bps[i] - 1024;
-        if (lim > c->smem_optin) lim = c->smem_optin;
+        if (lim > c->smem_optin - c->static_smem) lim = c->smem_optin - c->static_smem;
         out[i] = {thr[i], lim, bps[i], true};
     }
     out[4] = {512, 0, 2, false};
@@ -265,7 +292,8 @@ cudaError_t launch_chain_kernel(dicegp_ctx *c, const LaunchClass &lc, size_t sme
                                 const StreamArgs &sa, const int32_t *ids, int n_ids, int n_steps,
                                 int *queue) {
     auto kern = dicegp_chain_kernel<W_IN_SMEM>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(c->smem_optin - c->static_smem));
     if (e != cudaSuccess) return e;
     kern<<<grid, lc.threads, smem, st>>>(gt, ct, sa, ids, n_ids, n_steps, c->use_tma, queue);
     return cudaGetLastError();
@@ -341,7 +369,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             smem = std::max(smem, need);
         }
         smem = (smem + 127) & ~(size_t)127;
-        if (smem > c->smem_optin) return c->fail(DICEGP_ERR_LIMIT, "chain needs more shared memory than the device offers");
+        if (smem > c->smem_optin - c->static_smem) return c->fail(DICEGP_ERR_LIMIT, "chain needs more shared memory than the device offers");
         cudaStream_t st = c->class_stream[k];
         DG_CUDA(c, cudaStreamWaitEvent(st, c->ev_fork, 0));
         StreamArgs sak = sa;
@@ -423,6 +451,16 @@ int dicegp_create(int device, dicegp_ctx **out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
+    {
+        cudaFuncAttributes fa0, fa1;
+        if (cudaFuncGetAttributes(&fa0, dicegp_chain_kernel<false>) != cudaSuccess ||
+            cudaFuncGetAttributes(&fa1, dicegp_chain_kernel<true>) != cudaSuccess) {
+            g_last_error = std::string("kernel image not loadable on this device: ") + cudaGetErrorString(cudaGetLastError());
+            delete c;
+            return DICEGP_ERR_CUDA;
+        }
+        c->static_smem = std::max(fa0.sharedSizeBytes, fa1.sharedSizeBytes);
+    }
     const char *no_tma = getenv("DICEGP_NO_TMA");
     c->use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) goto fail;
