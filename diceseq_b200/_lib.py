@@ -11,11 +11,11 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdicegp.so")
+LIB_PATH = os.environ.get("DICEGP_LIB") or os.path.join(_HERE, "libdicegp.so")
 
 ABI_VERSION = 1
 
-CHAIN_RUNNING, CHAIN_CONVERGED, CHAIN_EXHAUSTED = 0, 1, 2
+CHAIN_RUNNING, CHAIN_CONVERGED, CHAIN_EXHAUSTED, CHAIN_NOMEM = 0, 1, 2, 3
 
 # every symbol include/dicegp.h declares (tests check that the library exports all of them)
 SYMBOLS = (
@@ -23,7 +23,7 @@ SYMBOLS = (
     "dicegp_get_limits", "dicegp_upload_genes", "dicegp_set_chains",
     "dicegp_main_chains_from_prerun", "dicegp_run_host_stream", "dicegp_run_device_stream",
     "dicegp_chain_status", "dicegp_download_trace", "dicegp_posterior_summary",
-    "dicegp_last_run_stats",
+    "dicegp_last_run_stats", "dicegp_set_trace_budget",
 )
 
 
@@ -79,6 +79,7 @@ def load():
     lib.dicegp_download_trace.argtypes = [vp, i32, i32, i32, pd, pd, pd, pd]
     lib.dicegp_posterior_summary.argtypes = [vp, i32, pi32, pd, pd, pi64, pd]
     lib.dicegp_last_run_stats.argtypes = [vp, pd, pi64, pi64, pi64]
+    lib.dicegp_set_trace_budget.argtypes = [vp, i64]
     for name in SYMBOLS:
         if name != "dicegp_last_error":
             getattr(lib, name).restype = C.c_int
@@ -207,6 +208,29 @@ class Context:
             self._h, int(chain), int(first_row), int(n_rows), _p(psi, C.c_double),
             _p(y, C.c_double), _p(pro, C.c_double), _p(lik, C.c_double)))
         return psi, y, pro, lik
+
+    def set_trace_budget(self, nbytes):
+        self._check(self.lib.dicegp_set_trace_budget(self._h, int(nbytes)))
+
+    def posterior_summary(self, chain_ids=None):
+        """Device-side burn-in summaries: (psi_mean list, psi_ci list, lik_marg array)."""
+        if chain_ids is None:
+            chain_ids = np.arange(len(self.chain_shapes))
+        ids = _i32(chain_ids)
+        sizes = np.array([self.chain_shapes[i][0] * self.chain_shapes[i][1] for i in ids], dtype=np.int64)
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        mean = np.empty(int(off[-1]))
+        ci = np.empty(2 * int(off[-1]))
+        lik = np.empty(ids.size)
+        self._check(self.lib.dicegp_posterior_summary(
+            self._h, ids.size, _p(ids, C.c_int32), _p(mean, C.c_double), _p(ci, C.c_double),
+            _p(off[:-1].copy(), C.c_int64), _p(lik, C.c_double)))
+        means, cis = [], []
+        for k, i in enumerate(ids):
+            Cn, Tc, _M = self.chain_shapes[i]
+            means.append(mean[off[k]:off[k + 1]].reshape(Cn, Tc))
+            cis.append(ci[2 * off[k]:2 * off[k + 1]].reshape(Cn, Tc, 2))
+        return means, cis, lik
 
     def last_run_stats(self):
         ms = C.c_double()

@@ -169,21 +169,23 @@ class BatchSampler:
             js_rows = [var[g, :int(packed.n_iso[g]) - 1] * 5 / (T * int(packed.n_iso[g]) * theta1) for g in range(G)]
             self._run_host(rng, js_rows, pf, T)
 
-        # 4. results
+        # 4. results: burn-in summaries are reduced on the device (run_utils.py:125-129)
         st = ctx.chain_status()
+        if (st["state"] == _lib.CHAIN_NOMEM).any():
+            raise MemoryError("%d chains ran out of trace memory; raise Context.set_trace_budget or "
+                              "use smaller batches" % int((st["state"] == _lib.CHAIN_NOMEM).sum()))
+        if summarize:
+            means, cis, lik = ctx.posterior_summary()
         out = []
         for g in range(G):
             r = GeneResult()
             r.m, r.cnt, r.state, r.flags = int(st["m"][g]), int(st["cnt"][g]), int(st["state"][g]), int(st["flags"][g])
             r.var = var[g, :int(packed.n_iso[g]) - 1].copy()
-            if summarize or keep_trace:
-                Psi, Y, Pro, Lik = ctx.download_trace(g, int(st["n_rows"][g]))
-                if summarize:
-                    b = int(r.m / 4)
-                    r.psi_mean = Psi[b:].mean(axis=0)
-                    r.psi_95 = [get_CI(Psi[b:, c, :], 0.95) for c in range(Psi.shape[1])]
-                    r.lik_marg = float(harmonic_mean_log(Lik[b:]))
-                if keep_trace:
-                    r.trace = (Psi, Y, Pro, Lik)
+            if summarize:
+                r.psi_mean = means[g]
+                r.psi_95 = [cis[g][c] for c in range(cis[g].shape[0])]
+                r.lik_marg = float(lik[g])
+            if keep_trace:
+                r.trace = ctx.download_trace(g, int(st["n_rows"][g]))
             out.append(r)
         return out

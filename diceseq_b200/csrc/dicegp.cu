@@ -16,6 +16,7 @@
 namespace dg {
 constexpr int DICEGP_CHAIN_CONVERGED_ = 1;
 constexpr int DICEGP_CHAIN_EXHAUSTED_ = 2;
+constexpr int DICEGP_CHAIN_NOMEM_ = 3;
 }  // namespace dg
 #include "dicegp_chain.cuh"
 
@@ -115,7 +116,8 @@ __global__ void dicegp_prerun_var_kernel(GeneTab gt, ChainTab ct, int G, double 
         const int b = (int)((double)m_ret / 4.0);
         const int n = n_rows - b;
         const int rowlen = 2 * C + 2;                       // Tc == 1
-        const double *y = ct.trace + ct.trace_off[chain] + (size_t)b * rowlen + C + c;
+        // pre-run traces (M = 100 rows) live in one page
+        const double *y = ct.trace + ct.ptab[ct.ptab_off[chain]] + (size_t)b * rowlen + C + c;
         double mean, ss;
         if (C == 2) {
             mean = dg_pw_global(y, n, rowlen) / (double)n;
@@ -138,6 +140,136 @@ __global__ void dicegp_prerun_var_kernel(GeneTab gt, ChainTab ct, int G, double 
         acc += ss / (double)n;
     }
     var_out[(size_t)g * DG_MAXC + c] = (acc + 0.000001) / (double)T;
+}
+
+// Copies rows [first, first+n) of one chain's paged trace into a dense (n x rowlen) buffer.
+__global__ void dicegp_gather_rows_kernel(ChainTab ct, int chain, int rowlen, int first, int n,
+                                          double *__restrict__ out) {
+    TraceView tv;
+    tv.pool = ct.trace; tv.tab = ct.ptab + ct.ptab_off[chain]; tv.shift = ct.pshift[chain]; tv.rowlen = rowlen;
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {
+        const double *src = tv.row(first + r);
+        for (int i = threadIdx.x; i < rowlen; i += blockDim.x) out[(size_t)r * rowlen + i] = __ldcg(src + i);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Posterior summary of one chain per block (run_utils.py:14-30, 125-129):
+//   burn-in b = int(m/4); psi_mean = Psi_all[b:].mean(0) (rows added sequentially, like
+//   numpy's axis-0 reduction); 95% interval = order statistics sorted[-k], sorted[k],
+//   k = int(n*(1-0.95)/2), found EXACTLY with an 8-bit radix select over the column held in
+//   shared memory; lik_marg = log n + min - log(sum exp(min - Lik)).
+// ---------------------------------------------------------------------------------------
+#define DG_SUM_THREADS 256
+__device__ unsigned long long dg_radix_select(const unsigned long long *keys, int n, int rank,
+                                              unsigned *hist, int *sh) {
+    // rank-th smallest (0-based) of n keys; hist: 256 bins; sh: 2 ints
+    unsigned long long prefix = 0, mask = 0;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long k = keys[i];
+            if ((k & mask) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // warp scan over 256 bins: 8 bins per lane
+            unsigned loc[8], tot = 0;
+            for (int j = 0; j < 8; ++j) { loc[j] = hist[threadIdx.x * 8 + j]; tot += loc[j]; }
+            unsigned incl = tot;
+            for (int off = 1; off < 32; off <<= 1) {
+                unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
+                if ((int)threadIdx.x >= off) incl += v;
+            }
+            unsigned before = incl - tot;
+            if ((unsigned)rank >= before && (unsigned)rank < incl) {
+                unsigned acc = before;
+                for (int j = 0; j < 8; ++j) {
+                    if ((unsigned)rank < acc + loc[j]) { sh[0] = threadIdx.x * 8 + j; sh[1] = rank - (int)acc; break; }
+                    acc += loc[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)(unsigned)sh[0] << shift;
+        mask |= 0xffull << shift;
+        rank = sh[1];
+        __syncthreads();
+    }
+    return prefix;
+}
+
+__global__ void __launch_bounds__(DG_SUM_THREADS)
+dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, double *__restrict__ mean_out,
+                      double *__restrict__ ci_out, const int64_t *__restrict__ out_off, double *__restrict__ lik_out) {
+    extern __shared__ __align__(16) unsigned long long dg_keys[];
+    __shared__ unsigned hist[256];
+    __shared__ int sh[2];
+    __shared__ double red[DG_SUM_THREADS / 32];
+    const int chain = ids[blockIdx.x];
+    const int C = gt.C[ct.gene[chain]], Tc = ct.Tc[chain], CT = C * Tc, rowlen = 2 * CT + 2;
+    const int state = ct.state[chain], m_ret = ct.m_ret[chain];
+    const int n_rows = state == dg::DICEGP_CHAIN_CONVERGED_ ? m_ret
+                       : (state == dg::DICEGP_CHAIN_EXHAUSTED_ ? ct.M[chain] : ct.m_next[chain]);
+    const int b = m_ret > 0 ? (m_ret >> 2) : 0;                   // int(m/4)
+    const int n = n_rows - b;
+    TraceView tv;
+    tv.pool = ct.trace; tv.tab = ct.ptab + ct.ptab_off[chain]; tv.shift = ct.pshift[chain]; tv.rowlen = rowlen;
+    double *mean = mean_out + out_off[blockIdx.x];
+    double *ci = ci_out + 2 * out_off[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (n <= 0) {
+        for (int i = tid; i < CT; i += blockDim.x) { mean[i] = nan(""); ci[2 * i] = nan(""); ci[2 * i + 1] = nan(""); }
+        if (tid == 0) lik_out[blockIdx.x] = nan("");
+        return;
+    }
+    // mean: one thread per column, rows in order
+    for (int col = tid; col < CT; col += blockDim.x) {
+        double a = 0.0;
+        int r = 0;
+        for (; r + 4 <= n; r += 4) {
+            const double v0 = __ldcg(tv.row(b + r) + col), v1 = __ldcg(tv.row(b + r + 1) + col);
+            const double v2 = __ldcg(tv.row(b + r + 2) + col), v3 = __ldcg(tv.row(b + r + 3) + col);
+            a += v0; a += v1; a += v2; a += v3;
+        }
+        for (; r < n; ++r) a += __ldcg(tv.row(b + r) + col);
+        mean[col] = a / (double)n;
+    }
+    // interval: per column radix select of ranks k and n-k (k = 0 -> both the minimum side quirk)
+    const int k = (int)((double)n * (1.0 - 0.95) / 2.0);
+    for (int col = 0; col < CT; ++col) {
+        __syncthreads();
+        for (int i = tid; i < n; i += blockDim.x)
+            dg_keys[i] = (unsigned long long)__double_as_longlong(__ldcg(tv.row(b + i) + col));
+        __syncthreads();
+        const unsigned long long lo = dg_radix_select(dg_keys, n, k, hist, sh);
+        const unsigned long long hi = dg_radix_select(dg_keys, n, k > 0 ? n - k : 0, hist, sh);
+        if (tid == 0) {
+            ci[2 * col] = __longlong_as_double((long long)hi);       // sorted[-k]
+            ci[2 * col + 1] = __longlong_as_double((long long)lo);   // sorted[k]
+        }
+    }
+    // harmonic-mean log-likelihood
+    double mn = INFINITY;
+    for (int i = tid; i < n; i += blockDim.x) mn = fmin(mn, __ldcg(tv.row(b + i) + 2 * CT + 1));
+    for (int off = 16; off > 0; off >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+    __syncthreads();
+    if (lane == 0) red[warp] = mn;
+    __syncthreads();
+    mn = red[0];
+    for (int w = 1; w < DG_SUM_THREADS / 32; ++w) mn = fmin(mn, red[w]);
+    double se = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) se += exp(mn - __ldcg(tv.row(b + i) + 2 * CT + 1));
+    for (int off = 16; off > 0; off >>= 1) se += __shfl_xor_sync(0xffffffffu, se, off);
+    __syncthreads();
+    if (lane == 0) red[warp] = se;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < DG_SUM_THREADS / 32; ++w) t += red[w];
+        lik_out[blockIdx.x] = log((double)n) + mn - log(t);
+    }
 }
 
 // =======================================================================================
@@ -194,10 +326,16 @@ struct dicegp_ctx {
     // chains
     int n_chains = 0;
     std::vector<dicegp_chain_desc> hdesc;
-    std::vector<int64_t> htrace_off, hst_off;
+    std::vector<int64_t> hptab_off, hst_off;
+    std::vector<int32_t> hpshift;
+    int64_t trace_budget_bytes = 0;      // 0 = default (a share of the free device memory)
+    int64_t pool_cap = 0;
     std::vector<int32_t> hchainC;
     DevBuf<int32_t> cgene, ct0, cTc, cM, cinit, cgap, cm_next, ccnt, cstate, cm_ret, cflags;
-    DevBuf<int64_t> ckinv, cpf, cjs, cjc, cy0, ctrace_off, cst_off, cstream_id;
+    DevBuf<int64_t> ckinv, cpf, cjs, cjc, cy0, cptab_off, cptab, cst_off, cstream_id;
+    DevBuf<int32_t> cpshift;
+    DevBuf<unsigned long long> cpool_head;
+    DevBuf<double> dgather;
     DevBuf<double> cprior, cpool, ctrace, cst;
     bool have_stream_id = false;
 
@@ -206,6 +344,7 @@ struct dicegp_ctx {
     DevBuf<int64_t> ddoff;
     DevBuf<double> ddelta, du, dvar;
     DevBuf<int> dqueue;
+    DevBuf<unsigned long long> dprof;
     double last_ms = 0.0;
     int64_t last_launches = 0, last_evals = 0, last_steps = 0;
     std::vector<int32_t> hm_next_before;
@@ -239,7 +378,9 @@ ChainTab make_chain_tab(dicegp_ctx *c) {
     t.gene = c->cgene.p; t.t0 = c->ct0.p; t.Tc = c->cTc.p; t.M = c->cM.p; t.initial = c->cinit.p;
     t.gap = c->cgap.p; t.kinv_off = c->ckinv.p; t.pf_off = c->cpf.p; t.js_off = c->cjs.p;
     t.jc_off = c->cjc.p; t.y0_off = c->cy0.p; t.prior_const = c->cprior.p; t.pool = c->cpool.p;
-    t.trace_off = c->ctrace_off.p; t.st_off = c->cst_off.p;
+    t.st_off = c->cst_off.p;
+    t.ptab_off = c->cptab_off.p; t.pshift = c->cpshift.p; t.ptab = c->cptab.p;
+    t.pool_head = c->cpool_head.p; t.pool_cap = c->pool_cap;
     t.stream_id = c->have_stream_id ? c->cstream_id.p : nullptr;
     t.trace = c->ctrace.p; t.st = c->cst.p; t.m_next = c->cm_next.p; t.cnt = c->ccnt.p;
     t.state = c->cstate.p; t.m_ret = c->cm_ret.p; t.flags = c->cflags.p;
@@ -352,6 +493,11 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     c->hm_next_before.resize(c->n_chains);
     DG_CUDA(c, cudaMemcpyAsync(c->hm_next_before.data(), c->cm_next.p, c->n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
 
+#ifdef DG_PROFILE
+    DG_CUDA(c, c->dprof.resize(16));
+    DG_CUDA(c, cudaMemsetAsync(c->dprof.p, 0, 16 * sizeof(unsigned long long), c->stream));
+    sa.prof = reinterpret_cast<const double *>(c->dprof.p);
+#endif
     GeneTab gt = make_gene_tab(c);
     ChainTab ct = make_chain_tab(c);
     DG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
@@ -412,6 +558,18 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
         evals += (ds + init_eval) * chain_reads(c, id);
     }
     c->last_ms = ms; c->last_launches = launches; c->last_evals = evals; c->last_steps = steps;
+#ifdef DG_PROFILE
+    {
+        unsigned long long h[16];
+        DG_CUDA(c, cudaMemcpy(h, c->dprof.p, sizeof h, cudaMemcpyDeviceToHost));
+        const char *nm[9] = {"propose", "exp+quad", "softmax", "lik", "lik-wait", "reduce", "decide", "update", "geweke"};
+        double n = (double)std::max<unsigned long long>(h[10], 1);
+        fprintf(stderr, "[dg_prof] steps=%llu cycles/step:", h[10]);
+        double tot = 0;
+        for (int i = 0; i < 9; ++i) { fprintf(stderr, " %s=%.0f", nm[i], h[i] / n); tot += h[i] / n; }
+        fprintf(stderr, " total=%.0f\n", tot);
+    }
+#endif
     return DICEGP_OK;
 }
 
@@ -487,7 +645,8 @@ int dicegp_destroy(dicegp_ctx *c) {
     c->cgene.release(); c->ct0.release(); c->cTc.release(); c->cM.release(); c->cinit.release();
     c->cgap.release(); c->cm_next.release(); c->ccnt.release(); c->cstate.release(); c->cm_ret.release();
     c->cflags.release(); c->ckinv.release(); c->cpf.release(); c->cjs.release(); c->cjc.release();
-    c->cy0.release(); c->ctrace_off.release(); c->cst_off.release(); c->cstream_id.release();
+    c->cy0.release(); c->cptab_off.release(); c->cptab.release(); c->cpshift.release(); c->cpool_head.release();
+    c->dgather.release(); c->cst_off.release(); c->cstream_id.release();
     c->cprior.release(); c->cpool.release(); c->ctrace.release(); c->cst.release();
     c->dids.release(); c->ddoff.release(); c->ddelta.release(); c->du.release(); c->dvar.release();
     c->dqueue.release();
@@ -566,12 +725,14 @@ static int install_chains(dicegp_ctx *c, int32_t n, const dicegp_chain_desc *des
                           int64_t pool_count, bool pool_on_device) {
     c->n_chains = 0;
     c->hdesc.assign(desc, desc + n);
-    c->htrace_off.assign(n, 0);
+    c->hptab_off.assign(n, 0);
+    c->hpshift.assign(n, 0);
     c->hst_off.assign(n, 0);
+    std::vector<int64_t> ptab;
     std::vector<int32_t> gene(n), t0(n), Tc(n), M(n), ini(n), gap(n);
     std::vector<int64_t> kinv(n), pf(n), js(n), jc(n), y0(n);
     std::vector<double> prior(n);
-    int64_t tr = 0, st = 0;
+    int64_t tr = 0, st = 0, worst = 0;
     for (int i = 0; i < n; ++i) {
         const dicegp_chain_desc &d = desc[i];
         if (d.gene < 0 || d.gene >= c->G) return c->fail(DICEGP_ERR_ARG, "set_chains: gene index out of range");
@@ -588,9 +749,18 @@ static int install_chains(dicegp_ctx *c, int32_t n, const dicegp_chain_desc *des
         gene[i] = d.gene; t0[i] = d.t0; Tc[i] = d.Tc; M[i] = d.M; ini[i] = d.initial; gap[i] = d.gap;
         kinv[i] = d.kinv_off; pf[i] = d.prop_factor_off; js[i] = d.jump_scale_off; jc[i] = d.jump_const_off;
         y0[i] = d.y0_off; prior[i] = d.prior_const;
-        c->htrace_off[i] = tr; c->hst_off[i] = st;
+        c->hst_off[i] = st;
         const int64_t rowlen = 2 * (int64_t)C * d.Tc + 2;
-        tr += rowlen * d.M;
+        // pages of 2^shift rows, at most 1024; the first page is allocated here
+        int shift = 0;
+        while ((1 << shift) < d.M && shift < 10) ++shift;
+        const int n_pages = (d.M + (1 << shift) - 1) >> shift;
+        c->hpshift[i] = shift;
+        c->hptab_off[i] = (int64_t)ptab.size();
+        ptab.push_back(tr);
+        for (int k = 1; k < n_pages; ++k) ptab.push_back(-1);
+        tr += rowlen << shift;
+        worst += (rowlen << shift) * n_pages;
         st += rowlen;
     }
 #define DG_RESIZE(buf, cnt) if ((buf).resize(cnt) != cudaSuccess) return c->fail(DICEGP_ERR_NOMEM, "set_chains: device allocation failed (" #buf ")")
@@ -598,13 +768,24 @@ static int install_chains(dicegp_ctx *c, int32_t n, const dicegp_chain_desc *des
     DG_RESIZE(c->cinit, n); DG_RESIZE(c->cgap, n); DG_RESIZE(c->cm_next, n); DG_RESIZE(c->ccnt, n);
     DG_RESIZE(c->cstate, n); DG_RESIZE(c->cm_ret, n); DG_RESIZE(c->cflags, n);
     DG_RESIZE(c->ckinv, n); DG_RESIZE(c->cpf, n); DG_RESIZE(c->cjs, n); DG_RESIZE(c->cjc, n);
-    DG_RESIZE(c->cy0, n); DG_RESIZE(c->ctrace_off, n); DG_RESIZE(c->cst_off, n); DG_RESIZE(c->cstream_id, n);
+    DG_RESIZE(c->cy0, n); DG_RESIZE(c->cst_off, n); DG_RESIZE(c->cstream_id, n);
     DG_RESIZE(c->cprior, n); DG_RESIZE(c->cst, st);
     if (!pool_on_device) DG_RESIZE(c->cpool, std::max<int64_t>(pool_count, 1));
-    if (c->ctrace.resize(tr) != cudaSuccess) {
-        char msg[160];
-        snprintf(msg, sizeof msg, "set_chains: cannot allocate %.1f GB of trace memory; use fewer chains per batch", tr * 8.0 / 1e9);
-        return c->fail(DICEGP_ERR_NOMEM, msg);
+    DG_RESIZE(c->cptab_off, n); DG_RESIZE(c->cpshift, n); DG_RESIZE(c->cptab, ptab.size()); DG_RESIZE(c->cpool_head, 1);
+    {
+        // trace pool: first pages + room for growth, bounded by the budget
+        size_t free_b = 0, total_b = 0;
+        DG_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+        free_b += c->ctrace.n * sizeof(double);                      // the old pool is reused / replaced
+        int64_t budget = c->trace_budget_bytes > 0 ? c->trace_budget_bytes : (int64_t)(free_b * 0.6);
+        int64_t cap = std::min<int64_t>(worst, std::max<int64_t>(budget / 8, tr));
+        if (c->ctrace.resize(cap) != cudaSuccess) {
+            char msg[200];
+            snprintf(msg, sizeof msg, "set_chains: cannot allocate %.1f GB of trace memory (first pages need %.1f GB); use fewer chains per batch",
+                     cap * 8.0 / 1e9, tr * 8.0 / 1e9);
+            return c->fail(DICEGP_ERR_NOMEM, msg);
+        }
+        c->pool_cap = cap;
     }
 #undef DG_RESIZE
     cudaStream_t s = c->stream;
@@ -612,7 +793,13 @@ static int install_chains(dicegp_ctx *c, int32_t n, const dicegp_chain_desc *des
     DG_UP(c->cgene, gene, int32_t); DG_UP(c->ct0, t0, int32_t); DG_UP(c->cTc, Tc, int32_t); DG_UP(c->cM, M, int32_t);
     DG_UP(c->cinit, ini, int32_t); DG_UP(c->cgap, gap, int32_t);
     DG_UP(c->ckinv, kinv, int64_t); DG_UP(c->cpf, pf, int64_t); DG_UP(c->cjs, js, int64_t); DG_UP(c->cjc, jc, int64_t);
-    DG_UP(c->cy0, y0, int64_t); DG_UP(c->ctrace_off, c->htrace_off, int64_t); DG_UP(c->cst_off, c->hst_off, int64_t);
+    DG_UP(c->cy0, y0, int64_t); DG_UP(c->cptab_off, c->hptab_off, int64_t); DG_UP(c->cst_off, c->hst_off, int64_t);
+    DG_UP(c->cpshift, c->hpshift, int32_t);
+    DG_CUDA(c, cudaMemcpyAsync(c->cptab.p, ptab.data(), ptab.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    {
+        unsigned long long head = (unsigned long long)tr;
+        DG_CUDA(c, cudaMemcpyAsync(c->cpool_head.p, &head, sizeof head, cudaMemcpyHostToDevice, s));
+    }
     DG_UP(c->cprior, prior, double);
 #undef DG_UP
     if (!pool_on_device && pool_count > 0)
@@ -779,7 +966,12 @@ int dicegp_download_trace(dicegp_ctx *c, int32_t chain, int32_t first_row, int32
     DG_CUDA(c, cudaSetDevice(c->device));
     const int CT = c->hC[d.gene] * d.Tc;
     const size_t rowlen = 2 * (size_t)CT + 2;
-    const double *src = c->ctrace.p + c->htrace_off[chain] + (size_t)first_row * rowlen;
+    DG_CUDA(c, c->dgather.resize((size_t)n_rows * rowlen));
+    dicegp_gather_rows_kernel<<<std::min(n_rows, 1184), 128, 0, c->stream>>>(make_chain_tab(c), chain, (int)rowlen,
+                                                                            first_row, n_rows, c->dgather.p);
+    DG_CUDA(c, cudaGetLastError());
+    DG_CUDA(c, cudaStreamSynchronize(c->stream));
+    const double *src = c->dgather.p;
     const size_t pitch = rowlen * sizeof(double);
     if (psi) DG_CUDA(c, cudaMemcpy2D(psi, CT * sizeof(double), src, pitch, CT * sizeof(double), n_rows, cudaMemcpyDeviceToHost));
     if (y) DG_CUDA(c, cudaMemcpy2D(y, CT * sizeof(double), src + CT, pitch, CT * sizeof(double), n_rows, cudaMemcpyDeviceToHost));
@@ -790,9 +982,62 @@ int dicegp_download_trace(dicegp_ctx *c, int32_t chain, int32_t first_row, int32
 
 int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids, double *psi_mean, double *psi_ci,
                              const int64_t *out_off, double *lik_marg) {
-    (void)n; (void)chain_ids; (void)psi_mean; (void)psi_ci; (void)out_off; (void)lik_marg;
     if (!c) return DICEGP_ERR_ARG;
-    return c->fail(DICEGP_ERR_STATE, "posterior_summary: not built yet (SURVEY.md 8(f)#1); download the trace");
+    if (c->n_chains == 0) return c->fail(DICEGP_ERR_STATE, "posterior_summary: no chains");
+    if (n <= 0 || !chain_ids || !psi_mean || !psi_ci || !out_off || !lik_marg)
+        return c->fail(DICEGP_ERR_ARG, "posterior_summary: NULL or empty argument");
+    DG_CUDA(c, cudaSetDevice(c->device));
+    int64_t total = 0;
+    size_t smem = 0;
+    for (int i = 0; i < n; ++i) {
+        const int id = chain_ids[i];
+        if (id < 0 || id >= c->n_chains) return c->fail(DICEGP_ERR_ARG, "posterior_summary: chain id out of range");
+        const dicegp_chain_desc &d = c->hdesc[id];
+        total = std::max<int64_t>(total, out_off[i] + (int64_t)c->hC[d.gene] * d.Tc);
+        smem = std::max(smem, (size_t)d.M * sizeof(unsigned long long));
+    }
+    if (smem > c->smem_optin - 2048) return c->fail(DICEGP_ERR_LIMIT, "posterior_summary: M too large for the shared-memory radix select");
+    // bound shared memory by the rows actually kept (lets short chains share an SM)
+    {
+        std::vector<int32_t> ids(chain_ids, chain_ids + n), mr(n), nr(n), st(n);
+        int rc = dicegp_chain_status(c, n, ids.data(), mr.data(), nr.data(), nullptr, st.data(), nullptr);
+        if (rc != DICEGP_OK) return rc;
+        int max_rows = 1;
+        for (int i = 0; i < n; ++i) max_rows = std::max(max_rows, nr[i]);
+        smem = (size_t)max_rows * sizeof(unsigned long long);
+    }
+    DevBuf<double> dmean, dci, dlik;
+    DevBuf<int64_t> doff;
+    DevBuf<int32_t> dids;
+    if (dmean.resize(total) != cudaSuccess || dci.resize(2 * total) != cudaSuccess || dlik.resize(n) != cudaSuccess ||
+        doff.resize(n) != cudaSuccess || dids.resize(n) != cudaSuccess) {
+        dmean.release(); dci.release(); dlik.release(); doff.release(); dids.release();
+        return c->fail(DICEGP_ERR_NOMEM, "posterior_summary: device allocation failed");
+    }
+    int rc = DICEGP_OK;
+    cudaError_t e;
+    do {
+        if ((e = cudaMemcpyAsync(doff.p, out_off, n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(dids.p, chain_ids, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
+        if ((e = cudaFuncSetAttribute(dicegp_summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - 2048))) != cudaSuccess) break;
+        dicegp_summary_kernel<<<n, DG_SUM_THREADS, smem, c->stream>>>(make_gene_tab(c), make_chain_tab(c), dids.p, dmean.p,
+                                                                       dci.p, doff.p, dlik.p);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(psi_mean, dmean.p, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(psi_ci, dci.p, 2 * total * sizeof(double), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(lik_marg, dlik.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(c->stream);
+    } while (0);
+    if (e != cudaSuccess) rc = c->cuda_fail(e, "posterior_summary");
+    dmean.release(); dci.release(); dlik.release(); doff.release(); dids.release();
+    return rc;
+}
+
+int dicegp_set_trace_budget(dicegp_ctx *c, int64_t bytes) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (bytes < 0) return c->fail(DICEGP_ERR_ARG, "set_trace_budget: negative budget");
+    c->trace_budget_bytes = bytes;
+    return DICEGP_OK;
 }
 
 int dicegp_last_run_stats(dicegp_ctx *c, double *kernel_ms, int64_t *launches, int64_t *read_evals, int64_t *steps) {

@@ -2,6 +2,16 @@
 #pragma once
 #include "dicegp_kernels.cuh"
 
+#ifdef DG_PROFILE
+#define DG_TICK(i) do { if (threadIdx.x == 0) { long long t__ = clock64(); dg_prof[i] += t__ - dg_t0; dg_t0 = t__; } } while (0)
+#define DG_PROF_ARGS , long long *dg_prof, long long &dg_t0
+#define DG_PROF_PASS , dg_prof, dg_t0
+#else
+#define DG_TICK(i) do { } while (0)
+#define DG_PROF_ARGS
+#define DG_PROF_PASS
+#endif
+
 namespace dg {
 
 // ---------------------------------------------------------------------------------------
@@ -95,7 +105,7 @@ struct ChainCtx {
 // (model_GP.py:335-337), GP prior (:332, normal_pdf :89-91), proposal density (:330-331)
 // and read likelihood (:338-345).  Results land in bc[0]=prior, bc[1]=Q, bc[2]=lik.
 // Every thread of the block must call it.
-__device__ __forceinline__ void evaluate(ChainCtx &s, bool with_q) {
+__device__ __forceinline__ void evaluate(ChainCtx &s, bool with_q DG_PROF_ARGS) {
     const int C = s.C, Tc = s.Tc, CT = s.CT, tid = s.tid;
     // phase 2: per (c,t): quadratic-form partials and exp
     if (tid < CT) {
@@ -115,6 +125,7 @@ __device__ __forceinline__ void evaluate(ChainCtx &s, bool with_q) {
         }
     }
     __syncthreads();
+    DG_TICK(1);
     // phase 3: per time point softmax + reweight; one thread sums prior and Q
     if (tid < Tc) {
         const int t = tid;
@@ -143,6 +154,7 @@ __device__ __forceinline__ void evaluate(ChainCtx &s, bool with_q) {
         s.bc[1] = Q;
     }
     __syncthreads();
+    DG_TICK(2);
     // phase 4: likelihood partials
     MantExp acc;
     acc.m = 1.0; acc.e = 0; acc.bad = 0u;
@@ -161,7 +173,9 @@ __device__ __forceinline__ void evaluate(ChainCtx &s, bool with_q) {
         s.redi[s.warp] = acc.e;
         s.redb[s.warp] = acc.bad;
     }
+    DG_TICK(3);
     __syncthreads();
+    DG_TICK(4);
     if (tid == 0) {
         double m = 1.0;
         long long e = 0;
@@ -171,6 +185,7 @@ __device__ __forceinline__ void evaluate(ChainCtx &s, bool with_q) {
         s.bc[3] = bad ? 1.0 : 0.0;
     }
     __syncthreads();
+    DG_TICK(5);
     if (s.bc[3] != 0.0) {
         // slow path: some read has a non-positive / non-finite likelihood term
         double ls = 0.0;
@@ -196,22 +211,20 @@ __device__ __forceinline__ void evaluate(ChainCtx &s, bool with_q) {
 // Two-pass mean / population variance like np.mean / np.var.  Lanes walk columns
 // (coalesced), warps walk rows.  Returns 1 to every thread when all |Z| <= 2.
 // ---------------------------------------------------------------------------------------
-// The trace is written by this very kernel: read it with ld.global.cg (L2), never through
-// the non-coherent path.
-__device__ __forceinline__ int geweke_converged(ChainCtx &s, const double *trace, int rowlen, int m) {
+__device__ __forceinline__ int geweke_converged(ChainCtx &s, const TraceView &tv, int m) {
     const int nA = (int)(0.1 * (double)m);
     const int iB = (int)(0.5 * (double)m);
     const int nB = m - iB;
     int ok = 1;
     for (int c0 = 0; c0 < s.CTm; c0 += DG_GW_COLS) {
         const int col = c0 + s.lane;
-        const bool act = (s.lane < DG_GW_COLS) && (col < s.CTm);
+        const bool act = col < s.CTm;
         double *gA = s.gw, *gB = s.gw + s.nwarps * DG_GW_COLS;
         // pass 1: sums
         double sa = 0.0, sb = 0.0;
         if (act) {
-            for (int r = s.warp; r < nA; r += s.nwarps) sa += __ldcg(trace + (size_t)r * rowlen + col);
-            for (int r = iB + s.warp; r < m; r += s.nwarps) sb += __ldcg(trace + (size_t)r * rowlen + col);
+            for (int r = s.warp; r < nA; r += s.nwarps) sa += __ldcg(tv.row(r) + col);
+            for (int r = iB + s.warp; r < m; r += s.nwarps) sb += __ldcg(tv.row(r) + col);
         }
         gA[s.warp * DG_GW_COLS + s.lane] = sa;
         gB[s.warp * DG_GW_COLS + s.lane] = sb;
@@ -228,11 +241,11 @@ __device__ __forceinline__ int geweke_converged(ChainCtx &s, const double *trace
         double qa = 0.0, qb = 0.0;
         if (act) {
             for (int r = s.warp; r < nA; r += s.nwarps) {
-                double d = __ldcg(trace + (size_t)r * rowlen + col) - meanA;
+                double d = __ldcg(tv.row(r) + col) - meanA;
                 qa = fma(d, d, qa);
             }
             for (int r = iB + s.warp; r < m; r += s.nwarps) {
-                double d = __ldcg(trace + (size_t)r * rowlen + col) - meanB;
+                double d = __ldcg(tv.row(r) + col) - meanB;
                 qb = fma(d, d, qb);
             }
         }
@@ -341,6 +354,11 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         const double *lens = gt.len + gt.lenoff[g] + (size_t)t0 * C;
         for (int i = s.tid; i < Tc * C; i += s.nthreads) s.lens[i] = lens[i];
     }
+#ifdef DG_PROFILE
+    long long dg_prof[10];
+    long long dg_t0 = 0;
+    long long *dg_prof_out = reinterpret_cast<long long *>(const_cast<double *>(sa.prof));
+#endif
     const int M = ct.M[chain], initial = ct.initial[chain], gap = ct.gap[chain];
     int m = ct.m_next[chain];
     int cnt = ct.cnt[chain];
@@ -348,7 +366,12 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     double *st = ct.st + ct.st_off[chain];
     double P_now = 0.0, L_now = 0.0;                      // live in thread 0
     const int rowlen = 2 * s.CT + 2;
-    double *trace = ct.trace + ct.trace_off[chain];
+    int64_t *ptab = ct.ptab + ct.ptab_off[chain];
+    const int pshift = ct.pshift[chain];
+    const int pmask = (1 << pshift) - 1;
+    TraceView tv;
+    tv.pool = ct.trace; tv.tab = ptab; tv.shift = pshift; tv.rowlen = rowlen;
+    double *page = nullptr;                               // base of the page holding row m
     const int64_t sid = ct.stream_id ? ct.stream_id[chain] : (int64_t)chain;
 
     if (m == 0) {
@@ -373,7 +396,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
 
     if (m == 0) {
         // initial state: P_now / L_now of the start value (model_GP.py:278-292)
-        evaluate(s, false);
+        evaluate(s, false DG_PROF_PASS);
         if (s.tid < s.CT) {
             s.ynow[s.tid] = s.ytry[s.tid];
             s.psinow[s.tid] = s.psitry[s.tid];
@@ -388,6 +411,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         __syncthreads();
     }
 
+    int state = 0, m_ret = 0;
     // ---- stream set-up ---------------------------------------------------------------------
     const int m_start = m;
     const int m_end = (m_start + n_steps < M) ? (m_start + n_steps) : M;
@@ -406,8 +430,34 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         __syncthreads();
     }
 
-    int state = 0, m_ret = 0;
+#ifdef DG_PROFILE
+    dg_t0 = clock64();
+    for (int i = 0; i < 10; ++i) dg_prof[i] = 0;
+#endif
     for (; m < m_end; ++m) {
+        // trace page of row m (allocated on first touch; the first page always exists)
+        if (page == nullptr || (m & pmask) == 0) {
+            if (s.tid == 0) {
+                long long e = __ldcg(ptab + (m >> pshift));
+                if (e < 0) {
+                    const unsigned long long need = (unsigned long long)rowlen << pshift;
+                    const unsigned long long off = atomicAdd(ct.pool_head, need);
+                    if (off + need <= (unsigned long long)ct.pool_cap) {
+                        e = (long long)off;
+                        ptab[m >> pshift] = e;
+                    }
+                }
+                s.bc[5] = __longlong_as_double(e);
+            }
+            __syncthreads();
+            const long long e = __double_as_longlong(s.bc[5]);
+            if (e < 0) {                                  // trace pool exhausted
+                state = DICEGP_CHAIN_NOMEM_;
+                m_ret = m - 1;
+                break;
+            }
+            page = ct.trace + e;
+        }
         // phase 1: proposal Y_try = delta + Y_now (model_GP.py:329; numpy adds the mean last)
         double u_cur = u_next;
         if (s.tid < s.CTm) {
@@ -435,7 +485,8 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             }
         }
         __syncthreads();
-        evaluate(s, true);
+        DG_TICK(0);
+        evaluate(s, true DG_PROF_PASS);
         // MH decision (model_GP.py:348-360), thread 0
         if (s.tid == 0) {
             const double lik = s.bc[2], Q = s.bc[1];
@@ -447,32 +498,42 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             if (!isfinite(P_try)) flags |= 1;
             if (acc) { P_now = P_try; L_now = lik; ++cnt; }
             s.bc[4] = acc ? 1.0 : 0.0;
-            double *row = trace + (size_t)m * rowlen;
+            double *row = page + (size_t)(m & pmask) * rowlen;
             row[2 * s.CT] = P_now;                             // Pro_all[m]  (:362)
             row[2 * s.CT + 1] = L_now;                         // Lik_all[m]  (:363)
         }
         __syncthreads();
+        DG_TICK(6);
         if (s.tid < s.CT) {
             if (s.bc[4] != 0.0) {
                 s.ynow[s.tid] = s.ytry[s.tid];
                 s.psinow[s.tid] = s.psitry[s.tid];
             }
-            double *row = trace + (size_t)m * rowlen;
+            double *row = page + (size_t)(m & pmask) * rowlen;
             row[s.tid] = s.psinow[s.tid];                      // Psi_all[m]  (:365)
             row[s.CT + s.tid] = s.ynow[s.tid];                 // Y_all[m]    (:364)
         }
         // convergence diagnostics (:369-391); the rows [0, m) exclude the one just written
         if (m >= initial && (m % gap) == 0) {
             __syncthreads();
-            if (geweke_converged(s, trace, rowlen, m)) {
+            DG_TICK(7);
+            if (geweke_converged(s, tv, m)) {
                 state = DICEGP_CHAIN_CONVERGED_;
                 m_ret = m;
                 ++m;
                 break;
             }
+            DG_TICK(8);
         }
         __syncthreads();
+        DG_TICK(7);
     }
+#ifdef DG_PROFILE
+    if (threadIdx.x == 0 && dg_prof_out) {
+        for (int i = 0; i < 10; ++i) atomicAdd((unsigned long long *)dg_prof_out + i, (unsigned long long)dg_prof[i]);
+        atomicAdd((unsigned long long *)dg_prof_out + 10, (unsigned long long)(m - m_start));
+    }
+#endif
     if (state == 0 && m >= M) { state = DICEGP_CHAIN_EXHAUSTED_; m_ret = M - 1; }
 
     // ---- save state ------------------------------------------------------------------------

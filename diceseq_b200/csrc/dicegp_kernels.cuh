@@ -37,9 +37,16 @@ struct ChainTab {
     const int64_t *kinv_off, *pf_off, *js_off, *jc_off, *y0_off;
     const double *prior_const;
     const double *pool;
-    const int64_t *trace_off;    // first double of the chain's trace
     const int64_t *st_off;       // first double of the chain's saved state
     const int64_t *stream_id;
+    // paged trace pool: a chain's rows live in pages of 2^shift rows; page p of chain i is
+    // at trace[ptab[ptab_off[i] + p]] (-1 = not allocated yet; the first page always is).
+    // Further pages are bump-allocated on the device as a chain grows.
+    const int64_t *ptab_off;
+    const int32_t *pshift;
+    int64_t *ptab;
+    unsigned long long *pool_head;   // next free double of the trace pool
+    int64_t pool_cap;                // doubles
     // mutable
     double *trace;
     double *st;                  // ynow[C*Tc], psinow[C*Tc], P_now, L_now
@@ -55,6 +62,22 @@ struct StreamArgs {
     // device stream (mode 1)
     uint64_t seed;
     int32_t mode;
+    const double *prof;          // DG_PROFILE builds: 16 x uint64 cycle counters (else NULL)
+};
+
+// Read-side view of one chain's paged trace.  The trace is written by the very kernel that
+// reads it back for the Geweke test: loads go through ld.global.cg (L2), never through
+// the non-coherent path.
+struct TraceView {
+    const double *pool;
+    const int64_t *tab;
+    int shift, rowlen;
+#ifdef __CUDACC__
+    __device__ __forceinline__ const double *row(int r) const {
+        const int64_t base = __ldcg(tab + (r >> shift));
+        return pool + base + (size_t)(r & ((1 << shift) - 1)) * rowlen;
+    }
+#endif
 };
 
 // ---------------------------------------------------------------------------------------

@@ -57,7 +57,9 @@ typedef struct dicegp_limits {
 enum dicegp_chain_state {
     DICEGP_CHAIN_RUNNING = 0,    /* more steps to do                                  */
     DICEGP_CHAIN_CONVERGED = 1,  /* Geweke rule met (model_GP.py:369-391)             */
-    DICEGP_CHAIN_EXHAUSTED = 2   /* reached M steps without converging                */
+    DICEGP_CHAIN_EXHAUSTED = 2,  /* reached M steps without converging                */
+    DICEGP_CHAIN_NOMEM = 3       /* stopped: the trace pool is full (raise the budget or
+                                    use fewer chains per batch); rows so far are kept   */
 };
 
 /* ------------------------------------------------------------------ lifetime ------- */
@@ -114,6 +116,16 @@ typedef struct dicegp_chain_desc {
     int64_t y0_off;           /* C*Tc doubles, or -1 for all zeros */
     double  prior_const;
 } dicegp_chain_desc;
+
+/*
+ * Trace memory.  The reference allocates M rows per call up front (model_GP.py:295-310);
+ * 10k genes x M=20000 would need >100 GB that way while most chains converge after
+ * 1-2k steps.  Traces therefore live in a paged pool: every chain gets its first page
+ * (<= 1024 rows) when it is created and grows page by page on the device.  The budget
+ * (bytes; 0 = 60% of the free device memory) caps the pool; a chain that cannot get a
+ * page stops with DICEGP_CHAIN_NOMEM.  Call before dicegp_set_chains.
+ */
+int dicegp_set_trace_budget(dicegp_ctx *ctx, int64_t bytes);
 
 /* Discards existing chains, creates n_chains new ones (ids 0..n-1), allocates traces. */
 int dicegp_set_chains(dicegp_ctx *ctx, int32_t n_chains, const dicegp_chain_desc *desc,

@@ -102,3 +102,42 @@ def test_host_stream_batch_runs_and_is_consistent(sampler):
         ll = _loglik_numpy(W_list, lens, Y[-1])
         assert abs(ll - Lik[-1]) <= 1e-12 * abs(ll)
         assert r.state in (1, 2) and r.cnt > 0
+
+
+def test_device_summary_matches_numpy(sampler):
+    """Posterior summary kernel vs the oracle's restatement of run_utils.py:125-131 on the
+    downloaded trace: mean (sequential axis-0 sum) and the order-statistic interval must be
+    bit-exact, the harmonic-mean log-likelihood within 1e-13 relative."""
+    genes = [90, 91, 92, 93, 94]
+    packed = _batch("timeseries", genes, reads=120, T=3)
+    res = sampler.run(packed, M=1700, initial=1000, gap=100, seed=11, gene_ids=genes, keep_trace=True)
+    for r in res:
+        Psi, Y, Pro, Lik = r.trace
+        psi_mean, psi_95, lik_marg, _ = orc.posterior_summary(Psi, Y, Lik, r.m)
+        assert np.array_equal(r.psi_mean, psi_mean)
+        for c in range(Psi.shape[1]):
+            assert np.array_equal(r.psi_95[c], psi_95[c])
+        assert abs(r.lik_marg - lik_marg) <= 1e-13 * abs(lik_marg)
+
+
+def test_trace_pool_grows_and_reports_exhaustion():
+    """Chains longer than their first page allocate pages on the device; a pool that is too
+    small stops the chain with CHAIN_NOMEM instead of corrupting memory."""
+    from diceseq_b200 import _lib
+    genes = [95, 96]
+    packed = _batch("static", genes, reads=100)
+    s = BatchSampler(0)
+    try:
+        res = s.run(packed, M=5000, initial=4000, gap=500, seed=1, gene_ids=genes, keep_trace=True)
+        for g, r in zip(genes, res):
+            W_list, lens = synth.gene_W("static", g, reads=100)
+            Psi, Y, Pro, Lik = r.trace
+            assert len(Lik) >= 4000
+            for row in (0, 1023, 1024, 2048, len(Lik) - 1):
+                ll = _loglik_numpy(W_list, lens, Y[row])
+                assert abs(ll - Lik[row]) <= 1e-12 * abs(ll)
+        s.ctx.set_trace_budget(2 * 1024 * 8 * 8)       # room for the first pages only
+        with pytest.raises(MemoryError):
+            s.run(packed, M=5000, initial=4000, gap=500, seed=1, gene_ids=genes)
+    finally:
+        s.close()
