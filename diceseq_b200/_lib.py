@@ -23,7 +23,8 @@ SYMBOLS = (
     "dicegp_get_limits", "dicegp_upload_genes", "dicegp_set_chains",
     "dicegp_main_chains_from_prerun", "dicegp_run_host_stream", "dicegp_run_device_stream",
     "dicegp_chain_status", "dicegp_download_trace", "dicegp_posterior_summary",
-    "dicegp_last_run_stats", "dicegp_set_trace_budget",
+    "dicegp_last_run_stats", "dicegp_set_trace_budget", "dicegp_set_prerun_chains",
+    "dicegp_timer_start", "dicegp_timer_stop", "dicegp_counters",
 )
 
 
@@ -80,6 +81,10 @@ def load():
     lib.dicegp_posterior_summary.argtypes = [vp, i32, pi32, pd, pd, pi64, pd]
     lib.dicegp_last_run_stats.argtypes = [vp, pd, pi64, pi64, pi64]
     lib.dicegp_set_trace_budget.argtypes = [vp, i64]
+    lib.dicegp_set_prerun_chains.argtypes = [vp, dbl, dbl, i32, i32, i32]
+    lib.dicegp_timer_start.argtypes = [vp]
+    lib.dicegp_timer_stop.argtypes = [vp, pd]
+    lib.dicegp_counters.argtypes = [vp, pi64, pi64, pi64]
     for name in SYMBOLS:
         if name != "dicegp_last_error":
             getattr(lib, name).restype = C.c_int
@@ -164,6 +169,23 @@ class Context:
         self._check(self.lib.dicegp_set_chains(self._h, len(descs), arr, _p(pool, C.c_double), pool.size))
         self.chain_shapes = [(int(self.gene_C[d.gene]), d.Tc, d.M) for d in descs]
 
+    def set_prerun_chains(self, theta1, var0=0.1, M=100, initial=100, gap=50):
+        self._check(self.lib.dicegp_set_prerun_chains(self._h, float(theta1), float(var0), M, initial, gap))
+        self.chain_shapes = [(int(c), 1, M) for c in self.gene_C for _ in range(self.T)]
+
+    def timer_start(self):
+        self._check(self.lib.dicegp_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self.lib.dicegp_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def counters(self):
+        a, b, d = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.dicegp_counters(self._h, C.byref(a), C.byref(b), C.byref(d)))
+        return {"kernel_launches": a.value, "h2d_bytes": b.value, "d2h_bytes": d.value}
+
     def main_chains_from_prerun(self, M, initial, gap, theta1, kinv, prop_factor, prior_const):
         kinv = _f64(kinv)
         pf = _f64(prop_factor) if prop_factor is not None else None
@@ -212,7 +234,7 @@ class Context:
     def set_trace_budget(self, nbytes):
         self._check(self.lib.dicegp_set_trace_budget(self._h, int(nbytes)))
 
-    def posterior_summary(self, chain_ids=None):
+    def posterior_summary(self, chain_ids=None, flat=False):
         """Device-side burn-in summaries: (psi_mean list, psi_ci list, lik_marg array)."""
         if chain_ids is None:
             chain_ids = np.arange(len(self.chain_shapes))
@@ -225,6 +247,8 @@ class Context:
         self._check(self.lib.dicegp_posterior_summary(
             self._h, ids.size, _p(ids, C.c_int32), _p(mean, C.c_double), _p(ci, C.c_double),
             _p(off[:-1].copy(), C.c_int64), _p(lik, C.c_double)))
+        if flat:
+            return mean, ci, lik, off
         means, cis = [], []
         for k, i in enumerate(ids):
             Cn, Tc, _M = self.chain_shapes[i]

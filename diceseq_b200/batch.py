@@ -4,7 +4,8 @@ for many genes at once on one GPU.
 Per gene the reference runs T single-time-point pre-runs (M=100, var=0.1) to set the jump
 variance, then the joint chain, then burn-in summaries.  Here all genes' pre-runs are one
 set of G*T chains, the jump variances are reduced on the device
-(`dicegp_main_chains_from_prerun`), and the G main chains run to Geweke convergence.
+(`dicegp_main_chains_from_prerun`), the G main chains run to Geweke convergence and the
+burn-in summaries are reduced on the device too (`dicegp_posterior_summary`).
 
 Random streams: `stream="device"` (default) uses the library's counter-based Philox
 stream keyed by (seed, global gene id, chain kind, step) -- results do not depend on how
@@ -40,58 +41,73 @@ def harmonic_mean_log(data):
 
 
 class GeneResult:
+    """What get_psi keeps of one gene's run (run_utils.py:123-131)."""
     __slots__ = ("m", "cnt", "state", "flags", "psi_mean", "psi_95", "lik_marg", "var", "trace")
 
     def __init__(self):
-        self.trace = None
+        self.psi_mean = self.psi_95 = self.lik_marg = self.trace = None
+
+
+class BatchResult:
+    """Flat per-batch arrays; indexing gives a GeneResult."""
+
+    def __init__(self, n_iso, T, status, var):
+        self.n_iso, self.T = n_iso, T
+        self.m, self.cnt = status["m"], status["cnt"]
+        self.state, self.flags, self.n_rows = status["state"], status["flags"], status["n_rows"]
+        self.var = var
+        self.psi_mean = self.psi_ci = self.lik_marg = self.off = None
+        self.traces = None
+
+    def __len__(self):
+        return len(self.n_iso)
+
+    def __getitem__(self, g):
+        if g < 0 or g >= len(self):
+            raise IndexError(g)
+        r = GeneResult()
+        C = int(self.n_iso[g])
+        r.m, r.cnt, r.state, r.flags = int(self.m[g]), int(self.cnt[g]), int(self.state[g]), int(self.flags[g])
+        r.var = self.var[g, :C - 1].copy()
+        if self.psi_mean is not None:
+            a, b = int(self.off[g]), int(self.off[g + 1])
+            r.psi_mean = self.psi_mean[a:b].reshape(C, self.T)
+            ci = self.psi_ci[2 * a:2 * b].reshape(C, self.T, 2)
+            r.psi_95 = [ci[c] for c in range(C)]
+            r.lik_marg = float(self.lik_marg[g])
+        if self.traces is not None:
+            r.trace = self.traces[g]
+        return r
+
+    def __iter__(self):
+        return (self[g] for g in range(len(self)))
+
+    def d2h_bytes(self):
+        n = sum(a.nbytes for a in (self.m, self.cnt, self.state, self.flags, self.n_rows))
+        if self.psi_mean is not None:
+            n += self.psi_mean.nbytes + self.psi_ci.nbytes + self.lik_marg.nbytes
+        return n + self.var.nbytes
 
 
 class BatchSampler:
-    """One GPU; `run` samples every gene of a PackedGenes batch."""
+    """One GPU.  `run` = `upload` + `sample`."""
 
     def __init__(self, device=0):
         self.ctx = _lib.Context(device)
         self.stats = {}
+        self.packed = None
 
     def close(self):
         self.ctx.close()
 
-    # -- chain construction ----------------------------------------------------------------
-    def _prerun_chains(self, packed, theta1, var0=0.1, M=100, initial=100, gap=50):
-        """G*T chains of one time point each (run_utils.py:111-114); chain g*T+j."""
-        K1 = np.array([[float(theta1)]])                 # GP_K of a single point
-        kinv1 = np.linalg.inv(K1)
-        prior_const = -(_LOG_2PI + np.log(np.linalg.det(K1))) / 2.0
-        pf1 = proposal_factor(K1)
-        pool = [kinv1.ravel(), pf1.ravel()]
-        off = 2
-        per_C = {}
-        for C in np.unique(packed.n_iso):
-            C = int(C)
-            js = np.full(max(C - 1, 0), var0 * 5 / (1 * C * theta1))
-            jc = np.array([-(_LOG_2PI + np.log(np.linalg.det(K1 * var0 * 5 / (1 * C * theta1)))) / 2.0] * max(C - 1, 0))
-            per_C[C] = (off, off + len(js))
-            pool += [js, jc]
-            off += 2 * len(js)
-        descs = []
-        for g in range(packed.G):
-            C = int(packed.n_iso[g])
-            jso, jco = per_C[C]
-            for j in range(packed.T):
-                descs.append(_lib.ChainDesc(gene=g, t0=j, Tc=1, M=M, initial=initial, gap=gap,
-                                            kinv_off=0, prop_factor_off=1, jump_scale_off=jso,
-                                            jump_const_off=jco, y0_off=-1, prior_const=float(prior_const)))
-        return descs, np.concatenate(pool)
-
     # -- host stream ---------------------------------------------------------------------
-    def _run_host(self, rng, js_rows, pf, T_chain):
+    def _run_host(self, rng, js_rows, pf, T_chain, ini, gap):
         """Advance all unfinished chains to the end with host-generated streams.
         js_rows[i]: jump scales (C-1,) of chain i; pf: (Tc,Tc) proposal factor."""
         ctx = self.ctx
         n = len(ctx.chain_shapes)
         active = np.arange(n)
         M = ctx.chain_shapes[0][2]
-        ini, gap = self._ini_gap
         start = 0
         for end in check_steps(M, ini, gap):
             while start < end and active.size:
@@ -107,50 +123,53 @@ class BatchSampler:
                 delta = np.concatenate(blocks) if blocks else np.zeros(0)
                 u = rng.random((active.size, S))
                 ctx.run_host_stream(active, S, delta, offs, u.ravel())
-                self._acc_stats()
+                self._acc_stats("main" if T_chain > 1 or M != 100 else "prerun")
                 start += S
             st = ctx.chain_status(active)
             active = active[st["state"] == _lib.CHAIN_RUNNING]
             if not active.size:
                 break
 
-    def _acc_stats(self):
+    def _acc_stats(self, phase):
         s = self.ctx.last_run_stats()
         for k, v in s.items():
             self.stats[k] = self.stats.get(k, 0) + v
+            self.stats[phase + "_" + k] = self.stats.get(phase + "_" + k, 0) + v
 
     # -- the pipeline ----------------------------------------------------------------------
-    def run(self, packed, X=None, theta1=3.0, theta2=None, M=20000, initial=1000, gap=100,
-            seed=0, gene_ids=None, stream="device", keep_trace=False, summarize=True):
-        ctx = self.ctx
+    def upload(self, packed):
+        """Host -> device copy of the packed gene batch (dicegp_upload_genes)."""
+        if not (packed.n_iso > 1).all():
+            raise ValueError("single-isoform genes never reach the sampler (run_utils.py:99-104); drop them first")
+        self.ctx.upload_genes(packed)
+        self.packed = packed
+
+    def sample(self, X=None, theta1=3.0, theta2=None, M=20000, initial=1000, gap=100, seed=0,
+               gene_ids=None, stream="device", keep_trace=False, summarize=True):
+        """Pre-runs -> jump variance -> joint chains -> summaries for the uploaded genes."""
+        ctx, packed = self.ctx, self.packed
         G, T = packed.G, packed.T
         X = np.arange(T) if X is None else np.asarray(X)
         if theta2 is None:
             theta2 = ((np.max(X) - np.min(X) + 0.1) / 3.0) ** 2       # diceseq.py:169
         gene_ids = np.arange(G, dtype=np.int64) if gene_ids is None else np.asarray(gene_ids, dtype=np.int64)
         self.stats = {}
-        multi = packed.n_iso > 1
-        if not multi.all():
-            raise ValueError("single-isoform genes never reach the sampler (run_utils.py:99-104); drop them first")
-        ctx.upload_genes(packed)
 
-        # 1. pre-runs
-        descs, pool = self._prerun_chains(packed, theta1)
-        ctx.set_chains(descs, pool)
+        # 1. pre-runs (run_utils.py:107-115)
+        ctx.set_prerun_chains(theta1, 0.1, 100, 100, 50)
         if stream == "device":
             sid = (gene_ids[:, None] * (T + 1) + np.arange(T)[None, :]).ravel()
             ctx.run_device_stream(seed, sid)
-            self._acc_stats()
+            self._acc_stats("prerun")
         else:
             rng = np.random.Generator(np.random.Philox(key=seed))
-            self._ini_gap = (100, 50)
             js_rows = []
             for g in range(G):
                 C = int(packed.n_iso[g])
                 js_rows += [np.full(C - 1, 0.1 * 5 / (1 * C * theta1))] * T
-            self._run_host(rng, js_rows, proposal_factor(np.array([[float(theta1)]])), 1)
+            self._run_host(rng, js_rows, np.array([[np.sqrt(theta1)]]), 1, 100, 50)
 
-        # 2. main chains from the pre-run variances (device reduction)
+        # 2. main chains from the pre-run variances (device reduction, run_utils.py:115-116)
         K = GP_K(X, [theta1, theta2])
         det = np.linalg.det(K)
         if det <= 0:
@@ -160,32 +179,26 @@ class BatchSampler:
         pf = proposal_factor(K)
         var = ctx.main_chains_from_prerun(M, initial, gap, theta1, kinv, pf, prior_const)
 
-        # 3. main run
+        # 3. main run (run_utils.py:120-122)
         if stream == "device":
             ctx.run_device_stream(seed, gene_ids * (T + 1) + T)
-            self._acc_stats()
+            self._acc_stats("main")
         else:
-            self._ini_gap = (initial, gap)
             js_rows = [var[g, :int(packed.n_iso[g]) - 1] * 5 / (T * int(packed.n_iso[g]) * theta1) for g in range(G)]
-            self._run_host(rng, js_rows, pf, T)
+            self._run_host(rng, js_rows, pf, T, initial, gap)
 
         # 4. results: burn-in summaries are reduced on the device (run_utils.py:125-129)
         st = ctx.chain_status()
         if (st["state"] == _lib.CHAIN_NOMEM).any():
             raise MemoryError("%d chains ran out of trace memory; raise Context.set_trace_budget or "
                               "use smaller batches" % int((st["state"] == _lib.CHAIN_NOMEM).sum()))
+        res = BatchResult(packed.n_iso, T, st, var)
         if summarize:
-            means, cis, lik = ctx.posterior_summary()
-        out = []
-        for g in range(G):
-            r = GeneResult()
-            r.m, r.cnt, r.state, r.flags = int(st["m"][g]), int(st["cnt"][g]), int(st["state"][g]), int(st["flags"][g])
-            r.var = var[g, :int(packed.n_iso[g]) - 1].copy()
-            if summarize:
-                r.psi_mean = means[g]
-                r.psi_95 = [cis[g][c] for c in range(cis[g].shape[0])]
-                r.lik_marg = float(lik[g])
-            if keep_trace:
-                r.trace = ctx.download_trace(g, int(st["n_rows"][g]))
-            out.append(r)
-        return out
+            res.psi_mean, res.psi_ci, res.lik_marg, res.off = ctx.posterior_summary(flat=True)
+        if keep_trace:
+            res.traces = [ctx.download_trace(g, int(st["n_rows"][g])) for g in range(G)]
+        return res
+
+    def run(self, packed, **kw):
+        self.upload(packed)
+        return self.sample(**kw)

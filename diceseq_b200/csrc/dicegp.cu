@@ -312,7 +312,8 @@ struct dicegp_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     cudaStream_t class_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[5] = {};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[5] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    int64_t total_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     int use_tma = 1;
 
     // genes
@@ -536,6 +537,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             e = launch_chain_kernel<false>(c, cls[k], smem, grid, st, gt, ct, sak, c->dids.p + base[k], n_ids, n_steps, queue);
         if (e != cudaSuccess) return c->cuda_fail(e, "chain kernel launch");
         ++launches;
+        ++c->total_launches;
         DG_CUDA(c, cudaEventRecord(c->ev_join[k], st));
         DG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[k], 0));
     }
@@ -627,6 +629,7 @@ int dicegp_create(int device, dicegp_ctx **out) {
         if (cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) goto fail;
     }
     if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) goto fail;
+    if (cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess) goto fail;
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) goto fail;
     *out = c;
     return DICEGP_OK;
@@ -653,6 +656,8 @@ int dicegp_destroy(dicegp_ctx *c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     for (int k = 0; k < 5; ++k) {
         if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
         if (c->class_stream[k]) cudaStreamDestroy(c->class_stream[k]);
@@ -717,6 +722,7 @@ int dicegp_upload_genes(dicegp_ctx *c, int32_t G, int32_t T, const int32_t *n_is
     if (w > 0) DG_CUDA(c, cudaMemcpyAsync(c->dW.p, W, w * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     DG_CUDA(c, cudaMemcpyAsync(c->dlen.p, len_iso, l * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     DG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->h2d_bytes += (w + l) * (int64_t)sizeof(double) + ((int64_t)G * (2 * T + 2) ) * 4 + (int64_t)G * 16;
     c->G = G; c->T = T;
     return DICEGP_OK;
 }
@@ -848,6 +854,7 @@ int dicegp_main_chains_from_prerun(dicegp_ctx *c, int32_t M, int32_t initial, in
         dicegp_prerun_var_kernel<<<(total + threads - 1) / threads, threads, 0, c->stream>>>(
             make_gene_tab(c), make_chain_tab(c), G, c->dvar.p);
         DG_CUDA(c, cudaGetLastError());
+        ++c->total_launches;
     }
     std::vector<double> var((size_t)G * DG_MAXC);
     DG_CUDA(c, cudaMemcpyAsync(var.data(), c->dvar.p, var.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -997,15 +1004,27 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
         smem = std::max(smem, (size_t)d.M * sizeof(unsigned long long));
     }
     if (smem > c->smem_optin - 2048) return c->fail(DICEGP_ERR_LIMIT, "posterior_summary: M too large for the shared-memory radix select");
-    // bound shared memory by the rows actually kept (lets short chains share an SM)
+    // Launch groups by rows kept: the radix select holds one column in shared memory, so
+    // short chains (the bulk) run 8 blocks per SM and only the long ones need a whole SM.
+    std::vector<int32_t> ids(chain_ids, chain_ids + n), nr(n);
     {
-        std::vector<int32_t> ids(chain_ids, chain_ids + n), mr(n), nr(n), st(n);
-        int rc = dicegp_chain_status(c, n, ids.data(), mr.data(), nr.data(), nullptr, st.data(), nullptr);
+        int rc = dicegp_chain_status(c, n, ids.data(), nullptr, nr.data(), nullptr, nullptr, nullptr);
         if (rc != DICEGP_OK) return rc;
-        int max_rows = 1;
-        for (int i = 0; i < n; ++i) max_rows = std::max(max_rows, nr[i]);
-        smem = (size_t)max_rows * sizeof(unsigned long long);
     }
+    const int bounds[4] = {3072, 7168, 14336, 0x7fffffff};
+    std::vector<int32_t> order;            // positions grouped by size class
+    int gstart[5] = {0, 0, 0, 0, 0}, gmax[4] = {1, 1, 1, 1};
+    for (int k = 0; k < 4; ++k) {
+        gstart[k] = (int)order.size();
+        for (int i = 0; i < n; ++i) {
+            const int lo = k == 0 ? -1 : bounds[k - 1];
+            if (nr[i] > lo && nr[i] <= bounds[k]) { order.push_back(i); gmax[k] = std::max(gmax[k], nr[i]); }
+        }
+    }
+    gstart[4] = (int)order.size();
+    std::vector<int32_t> ids_sorted(n);
+    std::vector<int64_t> off_sorted(n);
+    for (int i = 0; i < n; ++i) { ids_sorted[i] = chain_ids[order[i]]; off_sorted[i] = out_off[order[i]]; }
     DevBuf<double> dmean, dci, dlik;
     DevBuf<int64_t> doff;
     DevBuf<int32_t> dids;
@@ -1016,21 +1035,93 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
     }
     int rc = DICEGP_OK;
     cudaError_t e;
+    std::vector<double> lik_sorted(n);
     do {
-        if ((e = cudaMemcpyAsync(doff.p, out_off, n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(dids.p, chain_ids, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(doff.p, off_sorted.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(dids.p, ids_sorted.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
         if ((e = cudaFuncSetAttribute(dicegp_summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - 2048))) != cudaSuccess) break;
-        dicegp_summary_kernel<<<n, DG_SUM_THREADS, smem, c->stream>>>(make_gene_tab(c), make_chain_tab(c), dids.p, dmean.p,
-                                                                       dci.p, doff.p, dlik.p);
-        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        for (int k = 0; k < 4 && e == cudaSuccess; ++k) {
+            const int cnt = gstart[k + 1] - gstart[k];
+            if (cnt == 0) continue;
+            const size_t sm = (size_t)gmax[k] * sizeof(unsigned long long);
+            dicegp_summary_kernel<<<cnt, DG_SUM_THREADS, sm, c->stream>>>(make_gene_tab(c), make_chain_tab(c), dids.p + gstart[k],
+                                                                          dmean.p, dci.p, doff.p + gstart[k], dlik.p + gstart[k]);
+            ++c->total_launches;
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(psi_mean, dmean.p, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(psi_ci, dci.p, 2 * total * sizeof(double), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(lik_marg, dlik.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(lik_sorted.data(), dlik.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
         e = cudaStreamSynchronize(c->stream);
     } while (0);
     if (e != cudaSuccess) rc = c->cuda_fail(e, "posterior_summary");
+    else {
+        for (int i = 0; i < n; ++i) lik_marg[order[i]] = lik_sorted[i];
+        c->d2h_bytes += (3 * total + n) * (int64_t)sizeof(double);
+    }
     dmean.release(); dci.release(); dlik.release(); doff.release(); dids.release();
     return rc;
+}
+
+int dicegp_timer_start(dicegp_ctx *c) {
+    if (!c) return DICEGP_ERR_ARG;
+    DG_CUDA(c, cudaSetDevice(c->device));
+    DG_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+    return DICEGP_OK;
+}
+
+int dicegp_timer_stop(dicegp_ctx *c, double *ms) {
+    if (!c || !ms) return DICEGP_ERR_ARG;
+    DG_CUDA(c, cudaSetDevice(c->device));
+    DG_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    DG_CUDA(c, cudaEventSynchronize(c->ev_t1));
+    float f = 0.f;
+    DG_CUDA(c, cudaEventElapsedTime(&f, c->ev_t0, c->ev_t1));
+    *ms = f;
+    return DICEGP_OK;
+}
+
+int dicegp_counters(dicegp_ctx *c, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (kernel_launches) *kernel_launches = c->total_launches;
+    if (h2d_bytes) *h2d_bytes = c->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = c->d2h_bytes;
+    return DICEGP_OK;
+}
+
+int dicegp_set_prerun_chains(dicegp_ctx *c, double theta1, double var0, int32_t M, int32_t initial, int32_t gap) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (c->G == 0) return c->fail(DICEGP_ERR_STATE, "set_prerun_chains: upload genes first");
+    if (!(theta1 > 0) || !(var0 > 0)) return c->fail(DICEGP_ERR_ARG, "set_prerun_chains: theta1 and var0 must be positive");
+    DG_CUDA(c, cudaSetDevice(c->device));
+    // K = [[theta1]] (GP_K of one time point): inverse, determinant and svd factor are scalars
+    const double two_pi_log = std::log(2.0 * 3.14159265358979323846);
+    std::vector<double> pool;
+    pool.push_back(1.0 / theta1);                       // kinv
+    pool.push_back(std::sqrt(theta1));                  // z * sqrt(theta1) ~ N(0, K)
+    const double prior_const = -(two_pi_log + std::log(theta1)) / 2.0;
+    int64_t js_off[DG_MAXC + 1], jc_off[DG_MAXC + 1];
+    for (int C = 0; C <= DG_MAXC; ++C) js_off[C] = jc_off[C] = -1;
+    const int G = c->G, T = c->T;
+    std::vector<dicegp_chain_desc> desc((size_t)G * T);
+    for (int g = 0; g < G; ++g) {
+        const int C = c->hC[g];
+        if (js_off[C] < 0) {
+            const double cov = theta1 * var0 * 5 / (1 * C * theta1);      // model_GP.py:328 with T = 1
+            js_off[C] = (int64_t)pool.size();
+            for (int k = 0; k < C - 1; ++k) pool.push_back(var0 * 5 / (1 * C * theta1));
+            jc_off[C] = (int64_t)pool.size();
+            for (int k = 0; k < C - 1; ++k) pool.push_back(-(two_pi_log + std::log(cov)) / 2.0);
+        }
+        for (int j = 0; j < T; ++j) {
+            dicegp_chain_desc &d = desc[(size_t)g * T + j];
+            d.gene = g; d.t0 = j; d.Tc = 1; d.M = M; d.initial = initial; d.gap = gap;
+            d.kinv_off = 0; d.prop_factor_off = 1; d.jump_scale_off = js_off[C]; d.jump_const_off = jc_off[C];
+            d.y0_off = -1; d.prior_const = prior_const;
+        }
+    }
+    return install_chains(c, G * T, desc.data(), pool.data(), (int64_t)pool.size(), false);
 }
 
 int dicegp_set_trace_budget(dicegp_ctx *c, int64_t bytes) {

@@ -132,6 +132,14 @@ int dicegp_set_chains(dicegp_ctx *ctx, int32_t n_chains, const dicegp_chain_desc
                       const double *pool, int64_t pool_count);
 
 /*
+ * The pre-run chain set of get_psi (run_utils.py:107-114) for every uploaded gene, built
+ * inside the library: chain g*T+j = gene g, time point j alone (K = [[theta1]]), start 0,
+ * jump variance var0 (0.1 in the reference), M/initial/gap = 100/100/50 in the reference.
+ */
+int dicegp_set_prerun_chains(dicegp_ctx *ctx, double theta1, double var0, int32_t M,
+                             int32_t initial, int32_t gap);
+
+/*
  * Build the main-run chains from finished pre-run chains ON DEVICE: chain g*T+j must be
  * the pre-run of gene g, time j (M=100).  Computes
  *     var[c] = (sum_j Var(Y_j[int(m/4):, c, 0]) + 1e-6) / T       run_utils.py:115-116
@@ -202,6 +210,15 @@ int dicegp_posterior_summary(dicegp_ctx *ctx, int32_t n, const int32_t *chain_id
  * recent run_* call, and the MH steps x reads it evaluated.  For bench.py. */
 int dicegp_last_run_stats(dicegp_ctx *ctx, double *kernel_ms, int64_t *launches,
                           int64_t *read_evals, int64_t *steps);
+
+/* Device timer around any sequence of calls: CUDA events on the handle's launch stream
+ * (every kernel and copy of the library is ordered on, or joined to, that stream). */
+int dicegp_timer_start(dicegp_ctx *ctx);
+int dicegp_timer_stop(dicegp_ctx *ctx, double *elapsed_ms);
+
+/* Totals since dicegp_create: kernels launched, bytes uploaded with the gene batches. */
+int dicegp_counters(dicegp_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes,
+                    int64_t *d2h_bytes);
 
 #ifdef __cplusplus
 }
