@@ -26,14 +26,17 @@ constexpr int DICEGP_CHAIN_NOMEM_ = 3;
 // Static assignment (queue == nullptr): block b advances chain ids[b].
 // Persistent (queue != nullptr): blocks pull slots from an atomic counter until empty;
 // ids are sorted by decreasing cost so the heavy chains start first.
-template <bool W_IN_SMEM>
-__global__ void __launch_bounds__(DG_MAXTHREADS, 1)
+#ifndef DG_LB_THREADS
+#define DG_LB_THREADS DG_MAXTHREADS      // 1024 threads/SM -> 64 registers per thread
+#endif
+template <int KC, bool W_IN_SMEM>
+__global__ void __launch_bounds__(DG_LB_THREADS, 1)
 dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__restrict__ ids, int n_ids,
                     int n_steps, int use_tma, int *queue) {
     extern __shared__ __align__(128) double dg_smem[];
     if (queue == nullptr) {
         const int slot = blockIdx.x;
-        if (slot < n_ids) dg::run_chain<W_IN_SMEM>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma);
+        if (slot < n_ids) dg::run_chain<KC, W_IN_SMEM>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma);
         return;
     }
     __shared__ int next_slot;
@@ -43,7 +46,7 @@ dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__res
         const int slot = next_slot;
         __syncthreads();
         if (slot >= n_ids) break;
-        dg::run_chain<W_IN_SMEM>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma);
+        dg::run_chain<KC, W_IN_SMEM>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma);
         __syncthreads();
     }
 }
@@ -295,6 +298,8 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+constexpr int kStreams = 16;
+
 struct LaunchClass {
     int threads;
     size_t smem_limit;      // dynamic shared memory per block
@@ -311,8 +316,8 @@ struct dicegp_ctx {
     size_t static_smem = 0;      // static shared memory of the chain kernel
     std::string err;
     cudaStream_t stream = nullptr;
-    cudaStream_t class_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[5] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaStream_t class_stream[16] = {};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[40] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     int64_t total_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     int use_tma = 1;
 
@@ -388,8 +393,13 @@ ChainTab make_chain_tab(dicegp_ctx *c) {
     return t;
 }
 
-// launch classes: W resident at 8/4/2/1 blocks per SM, then the streaming class
-void launch_classes(const dicegp_ctx *c, LaunchClass out[5]) {
+// Residency tiers: W resident in shared memory at 8/4/2/1 blocks per SM, then the tier
+// that streams W from L2/HBM every step.  Each tier is further split by isoform count,
+// because the likelihood loop is compiled per C (weights f[C] in registers).
+constexpr int kTiers = 5;
+constexpr int kKinds = 8;                      // kernel variants by C: generic, 2..8
+constexpr int kGroups = kTiers * kKinds;
+void launch_classes(const dicegp_ctx *c, LaunchClass out[kTiers]) {
     const size_t per_sm = 233472;  // 228 KB
     const int bps[4] = {8, 4, 2, 1};
     const int thr[4] = {128, 256, 512, 1024};
@@ -398,7 +408,16 @@ void launch_classes(const dicegp_ctx *c, LaunchClass out[5]) {
         if (lim > c->smem_optin - c->static_smem) lim = c->smem_optin - c->static_smem;
         out[i] = {thr[i], lim, bps[i], true};
     }
-    out[4] = {512, 0, 2, false};
+    out[4] = {256, 0, 4, false};
+    // development overrides: DICEGP_TIER_THREADS / DICEGP_TIER_BPS = five comma-separated ints
+    const char *et = getenv("DICEGP_TIER_THREADS"), *eb = getenv("DICEGP_TIER_BPS");
+    if (et) sscanf(et, "%d,%d,%d,%d,%d", &out[0].threads, &out[1].threads, &out[2].threads, &out[3].threads, &out[4].threads);
+    if (eb) sscanf(eb, "%d,%d,%d,%d,%d", &out[0].blocks_per_sm, &out[1].blocks_per_sm, &out[2].blocks_per_sm, &out[3].blocks_per_sm, &out[4].blocks_per_sm);
+    for (int i = 0; i < kTiers; ++i) {
+        if (out[i].threads > DG_LB_THREADS) out[i].threads = DG_LB_THREADS;
+        // register file: DG_LB_THREADS threads per SM at the compiled register count
+        if (out[i].threads * out[i].blocks_per_sm > DG_LB_THREADS) out[i].blocks_per_sm = DG_LB_THREADS / out[i].threads;
+    }
 }
 
 size_t fixed_smem_bytes(int C, int Tc, int threads) {
@@ -417,69 +436,80 @@ int64_t chain_wbytes(const dicegp_ctx *c, int chain) {
     return (int64_t)c->hC[d.gene] * (ro[d.Tc] - ro[0]) * 8;
 }
 
-int pick_class(const dicegp_ctx *c, const LaunchClass cls[5], int chain) {
+inline int kind_of(int C) { return (C >= 2 && C <= 8) ? C - 1 : 0; }
+
+// threads a chain needs at least: its state warps plus one likelihood warp
+inline int min_threads(int C, int Tc) { return ((C * Tc + 31) / 32) * 32 + 32; }
+
+int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain) {
     const dicegp_chain_desc &d = c->hdesc[chain];
     const int C = c->hC[d.gene];
     const int64_t wb = chain_wbytes(c, chain);
     for (int i = 0; i < 4; ++i) {
-        if (cls[i].threads < C * d.Tc) continue;
+        if (cls[i].threads < min_threads(C, d.Tc)) continue;
         if (fixed_smem_bytes(C, d.Tc, cls[i].threads) + (size_t)wb <= cls[i].smem_limit) return i;
     }
     return 4;
 }
 
-template <bool W_IN_SMEM>
-cudaError_t launch_chain_kernel(dicegp_ctx *c, const LaunchClass &lc, size_t smem, int grid,
-                                cudaStream_t st, const GeneTab &gt, const ChainTab &ct,
-                                const StreamArgs &sa, const int32_t *ids, int n_ids, int n_steps,
-                                int *queue) {
-    auto kern = dicegp_chain_kernel<W_IN_SMEM>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(c->smem_optin - c->static_smem));
-    if (e != cudaSuccess) return e;
-    kern<<<grid, lc.threads, smem, st>>>(gt, ct, sa, ids, n_ids, n_steps, c->use_tma, queue);
-    return cudaGetLastError();
+typedef void (*chain_kernel_t)(GeneTab, ChainTab, StreamArgs, const int32_t *, int, int, int, int *);
+chain_kernel_t chain_kernel_for(int kind, bool w_in_smem) {
+    switch (kind * 2 + (w_in_smem ? 1 : 0)) {
+        case 0: return dicegp_chain_kernel<0, false>;   case 1: return dicegp_chain_kernel<0, true>;
+        case 2: return dicegp_chain_kernel<2, false>;   case 3: return dicegp_chain_kernel<2, true>;
+        case 4: return dicegp_chain_kernel<3, false>;   case 5: return dicegp_chain_kernel<3, true>;
+        case 6: return dicegp_chain_kernel<4, false>;   case 7: return dicegp_chain_kernel<4, true>;
+        case 8: return dicegp_chain_kernel<5, false>;   case 9: return dicegp_chain_kernel<5, true>;
+        case 10: return dicegp_chain_kernel<6, false>;  case 11: return dicegp_chain_kernel<6, true>;
+        case 12: return dicegp_chain_kernel<7, false>;  case 13: return dicegp_chain_kernel<7, true>;
+        case 14: return dicegp_chain_kernel<8, false>;  default: return dicegp_chain_kernel<8, true>;
+    }
 }
 
 // Common driver: advance `ids` (host order) by n_steps with stream args `sa`.
-// slot_of[i] gives the host-stream slot of ids[i] (host mode) -- the kernel's slot is the
-// position in the per-class id list, so the per-slot offsets are permuted alongside.
+// The kernel's slot is the position in the per-group id list, so the per-slot host-stream
+// offsets are permuted alongside.
 int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, StreamArgs sa,
                const std::vector<int64_t> *delta_off, bool persistent) {
-    LaunchClass cls[5];
+    LaunchClass cls[kTiers];
     launch_classes(c, cls);
-    std::vector<int32_t> by_class[5];
-    std::vector<int32_t> slot_src[5];
+    std::vector<int32_t> by_group[kGroups];
+    std::vector<int32_t> slot_src[kGroups];
     for (size_t i = 0; i < ids.size(); ++i) {
-        int k = pick_class(c, cls, ids[i]);
-        by_class[k].push_back(ids[i]);
+        const dicegp_chain_desc &d = c->hdesc[ids[i]];
+        const int C = c->hC[d.gene];
+        int tier = pick_tier(c, cls, ids[i]);
+        if (tier == 4 && cls[4].threads < min_threads(C, d.Tc))
+            return c->fail(DICEGP_ERR_LIMIT, "chain has too many latent values for the streaming tier");
+        const int k = tier * kKinds + kind_of(C);
+        by_group[k].push_back(ids[i]);
         slot_src[k].push_back((int32_t)i);
     }
     if (persistent) {
         // heavy chains first (cost ~ C * reads)
-        for (int k = 0; k < 5; ++k) {
+        for (int k = 0; k < kGroups; ++k) {
             std::vector<std::pair<int64_t, int32_t>> key;
-            for (int32_t id : by_class[k]) key.push_back({-chain_wbytes(c, id), id});
-            std::sort(key.begin(), key.end());
-            for (size_t i = 0; i < key.size(); ++i) by_class[k][i] = key[i].second;
+            for (int32_t id : by_group[k]) key.push_back({-chain_wbytes(c, id), id});
+            std::stable_sort(key.begin(), key.end());
+            for (size_t i = 0; i < key.size(); ++i) by_group[k][i] = key[i].second;
         }
     }
     // flatten ids (and permuted host-stream offsets) into one device array
     std::vector<int32_t> flat;
     std::vector<int64_t> flat_doff;   // [0, n): delta offsets, [n, 2n): u offsets, kernel-slot order
     std::vector<int64_t> flat_uoff;
-    size_t base[6] = {0};
-    for (int k = 0; k < 5; ++k) {
+    size_t base[kGroups + 1] = {0};
+    for (int k = 0; k < kGroups; ++k) {
         base[k] = flat.size();
-        for (size_t i = 0; i < by_class[k].size(); ++i) {
-            flat.push_back(by_class[k][i]);
+        for (size_t i = 0; i < by_group[k].size(); ++i) {
+            flat.push_back(by_group[k][i]);
             if (delta_off) {
                 flat_doff.push_back((*delta_off)[slot_src[k][i]]);
                 flat_uoff.push_back((int64_t)slot_src[k][i] * n_steps);
             }
         }
     }
-    base[5] = flat.size();
+    base[kGroups] = flat.size();
     DG_CUDA(c, c->dids.resize(flat.size()));
     DG_CUDA(c, cudaMemcpyAsync(c->dids.p, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     if (delta_off) {
@@ -487,8 +517,8 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
         DG_CUDA(c, c->ddoff.resize(flat_doff.size()));
         DG_CUDA(c, cudaMemcpyAsync(c->ddoff.p, flat_doff.data(), flat_doff.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     }
-    DG_CUDA(c, c->dqueue.resize(8));
-    DG_CUDA(c, cudaMemsetAsync(c->dqueue.p, 0, 8 * sizeof(int), c->stream));
+    DG_CUDA(c, c->dqueue.resize(kGroups));
+    DG_CUDA(c, cudaMemsetAsync(c->dqueue.p, 0, kGroups * sizeof(int), c->stream));
 
     // steps bookkeeping for the stats (m_next before)
     c->hm_next_before.resize(c->n_chains);
@@ -504,42 +534,52 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     DG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     DG_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
     int64_t launches = 0;
-    for (int k = 0; k < 5; ++k) {
-        const int n_ids = (int)by_class[k].size();
-        if (n_ids == 0) continue;
-        // dynamic shared memory of this launch: the largest need among its chains
-        size_t smem = 0;
-        for (int32_t id : by_class[k]) {
-            const dicegp_chain_desc &d = c->hdesc[id];
-            size_t need = fixed_smem_bytes(c->hC[d.gene], d.Tc, cls[k].threads);
-            if (cls[k].w_in_smem) need += (size_t)chain_wbytes(c, id);
-            smem = std::max(smem, need);
+    int next_stream = 0;
+    // big tiers first: the 1-block-per-SM and streaming launches carry most of the work
+    const int tier_order[kTiers] = {4, 3, 2, 1, 0};
+    for (int to = 0; to < kTiers; ++to) {
+        for (int kind = 0; kind < kKinds; ++kind) {
+            const int tier = tier_order[to];
+            const int k = tier * kKinds + kind;
+            const int n_ids = (int)by_group[k].size();
+            if (n_ids == 0) continue;
+            // dynamic shared memory of this launch: the largest need among its chains
+            size_t smem = 0;
+            for (int32_t id : by_group[k]) {
+                const dicegp_chain_desc &d = c->hdesc[id];
+                size_t need = fixed_smem_bytes(c->hC[d.gene], d.Tc, cls[tier].threads);
+                if (cls[tier].w_in_smem) need += (size_t)chain_wbytes(c, id);
+                smem = std::max(smem, need);
+            }
+            smem = (smem + 127) & ~(size_t)127;
+            if (smem > c->smem_optin - c->static_smem) return c->fail(DICEGP_ERR_LIMIT, "chain needs more shared memory than the device offers");
+            cudaStream_t st = c->class_stream[next_stream];
+            next_stream = (next_stream + 1) % kStreams;
+            DG_CUDA(c, cudaStreamWaitEvent(st, c->ev_fork, 0));
+            StreamArgs sak = sa;
+            if (delta_off) {
+                sak.delta_off = c->ddoff.p + base[k];
+                sak.u_off = c->ddoff.p + flat.size() + base[k];
+            }
+            int grid = n_ids;
+            int *queue = nullptr;
+            if (persistent) {
+                grid = std::min(n_ids, c->sm_count * cls[tier].blocks_per_sm);
+                queue = c->dqueue.p + k;
+            }
+            chain_kernel_t kern = chain_kernel_for(kind, cls[tier].w_in_smem);
+            DG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(c->smem_optin - c->static_smem)));
+            kern<<<grid, cls[tier].threads, smem, st>>>(gt, ct, sak, c->dids.p + base[k], n_ids, n_steps, c->use_tma, queue);
+            {
+                cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess) return c->cuda_fail(e, "chain kernel launch");
+            }
+            ++launches;
+            ++c->total_launches;
+            DG_CUDA(c, cudaEventRecord(c->ev_join[k], st));
+            DG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[k], 0));
         }
-        smem = (smem + 127) & ~(size_t)127;
-        if (smem > c->smem_optin - c->static_smem) return c->fail(DICEGP_ERR_LIMIT, "chain needs more shared memory than the device offers");
-        cudaStream_t st = c->class_stream[k];
-        DG_CUDA(c, cudaStreamWaitEvent(st, c->ev_fork, 0));
-        StreamArgs sak = sa;
-        if (delta_off) {
-            sak.delta_off = c->ddoff.p + base[k];
-            sak.u_off = c->ddoff.p + flat.size() + base[k];
-        }
-        int grid = n_ids;
-        int *queue = nullptr;
-        if (persistent) {
-            grid = std::min(n_ids, c->sm_count * cls[k].blocks_per_sm);
-            queue = c->dqueue.p + k;
-        }
-        cudaError_t e;
-        if (cls[k].w_in_smem)
-            e = launch_chain_kernel<true>(c, cls[k], smem, grid, st, gt, ct, sak, c->dids.p + base[k], n_ids, n_steps, queue);
-        else
-            e = launch_chain_kernel<false>(c, cls[k], smem, grid, st, gt, ct, sak, c->dids.p + base[k], n_ids, n_steps, queue);
-        if (e != cudaSuccess) return c->cuda_fail(e, "chain kernel launch");
-        ++launches;
-        ++c->total_launches;
-        DG_CUDA(c, cudaEventRecord(c->ev_join[k], st));
-        DG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[k], 0));
     }
     DG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     DG_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -613,8 +653,8 @@ int dicegp_create(int device, dicegp_ctx **out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     {
         cudaFuncAttributes fa0, fa1;
-        if (cudaFuncGetAttributes(&fa0, dicegp_chain_kernel<false>) != cudaSuccess ||
-            cudaFuncGetAttributes(&fa1, dicegp_chain_kernel<true>) != cudaSuccess) {
+        if (cudaFuncGetAttributes(&fa0, dicegp_chain_kernel<0, false>) != cudaSuccess ||
+            cudaFuncGetAttributes(&fa1, dicegp_chain_kernel<0, true>) != cudaSuccess) {
             g_last_error = std::string("kernel image not loadable on this device: ") + cudaGetErrorString(cudaGetLastError());
             delete c;
             return DICEGP_ERR_CUDA;
@@ -624,10 +664,10 @@ int dicegp_create(int device, dicegp_ctx **out) {
     const char *no_tma = getenv("DICEGP_NO_TMA");
     c->use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) goto fail;
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < kStreams; ++k)
         if (cudaStreamCreateWithFlags(&c->class_stream[k], cudaStreamNonBlocking) != cudaSuccess) goto fail;
+    for (int k = 0; k < 40; ++k)
         if (cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) goto fail;
-    }
     if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) goto fail;
     if (cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess) goto fail;
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) goto fail;
@@ -658,10 +698,10 @@ int dicegp_destroy(dicegp_ctx *c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < 40; ++k)
         if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+    for (int k = 0; k < kStreams; ++k)
         if (c->class_stream[k]) cudaStreamDestroy(c->class_stream[k]);
-    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return DICEGP_OK;

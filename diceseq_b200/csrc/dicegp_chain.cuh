@@ -1,208 +1,151 @@
-// dicegp_chain.cuh -- the per-chain MH loop (one thread block per chain).
+// dicegp_chain.cuh -- the per-chain MH loop (one thread block per chain), kernel v1.
+//
+// Warp-specialised: the first S = ceil(C*Tc/32) warps are STATE warps, one thread per
+// latent value y[c,t]; they own the serial part of a step (proposal, softmax / length
+// reweighting, GP prior, MH decision, trace row).  The remaining warps are LIKELIHOOD
+// warps; each owns fixed read slices of fixed time points, keeps that time point's
+// isoform weights f in registers and accumulates prod(x_n) as (mantissa, exponent).
+// Per step the two groups meet at three block barriers (B1: f is ready, B2: partial
+// likelihoods are ready, B3: decision is known); the rest of the serial part overlaps
+// with the likelihood pass, and the device-generated random stream for step m+2 is
+// produced by the likelihood warps while the state warps write the trace row of step m.
 #pragma once
 #include "dicegp_kernels.cuh"
 
 #ifdef DG_PROFILE
 #define DG_TICK(i) do { if (threadIdx.x == 0) { long long t__ = clock64(); dg_prof[i] += t__ - dg_t0; dg_t0 = t__; } } while (0)
-#define DG_PROF_ARGS , long long *dg_prof, long long &dg_t0
-#define DG_PROF_PASS , dg_prof, dg_t0
 #else
 #define DG_TICK(i) do { } while (0)
-#define DG_PROF_ARGS
-#define DG_PROF_PASS
 #endif
 
 namespace dg {
 
-// ---------------------------------------------------------------------------------------
-// read likelihood: sum_t sum_n log(sum_k W_t[n,k] f_t[k])        model_GP.py:338,344-345
-// W block of time tt: isoform-major, row k = npad doubles, npad even.  Each thread takes
-// read PAIRS (one 16-byte load per isoform), consecutive threads consecutive pairs:
-// conflict-free LDS.128 / fully coalesced LDG.128.
-// ---------------------------------------------------------------------------------------
+// named barrier 2: state warps only (barrier 0 = __syncthreads)
+__device__ __forceinline__ void bar_state(int nstate) {
+    asm volatile("bar.sync 2, %0;" ::"r"(nstate) : "memory");
+}
+
+// One likelihood segment: pairs p = p0, p0+stride, ... of one time point.
+//   x_n = sum_k W[n,k] f[k]                                    model_GP.py:338
+// W block: isoform-major, row k = npairs double2 (two reads per 16-byte load; consecutive
+// lanes take consecutive pairs: conflict-free LDS.128 / coalesced LDG.128).
+// prod(x) is carried as two mantissa products (one per read of the pair) and one
+// exponent sum; anything that is not a positive normal double raises `bad`.
 template <int KC, bool LOGPATH>
-__device__ __forceinline__ void lik_partial(const double *__restrict__ Wc, int C, int Tc,
-                                            const int *rel, const int *ncnt,
-                                            const double *fsi, int tid, int nthreads,
-                                            MantExp &acc, double &logsum) {
+__device__ __forceinline__ void lik_segment(const double2 *__restrict__ Wt, int npairs, int n, int C,
+                                            const double *fcol, int Tc, int p0, int stride, double &m0,
+                                            double &m1, int &e, unsigned &bad, double &logsum) {
     constexpr int KR = KC > 0 ? KC : 1;
+    double f[KR];
+    if (KC > 0) {
+#pragma unroll
+        for (int k = 0; k < KR; ++k) f[k] = fcol[k * Tc];
+    }
     int it = 0;
-    for (int tt = 0; tt < Tc; ++tt) {
-        const int r0 = rel[tt];
-        const int npairs = (rel[tt + 1] - r0) >> 1;
-        const int n = ncnt[tt];
-        const double2 *__restrict__ Wt = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0);
-        double f[KR];
+#pragma unroll 2
+    for (int p = p0; p < npairs; p += stride) {
+        double x0 = 0.0, x1 = 0.0;
         if (KC > 0) {
 #pragma unroll
-            for (int k = 0; k < KR; ++k) f[k] = fsi[k * Tc + tt];
-        }
-        for (int p = tid; p < npairs; p += nthreads) {
-            double x0 = 0.0, x1 = 0.0;
-            if (KC > 0) {
-#pragma unroll
-                for (int k = 0; k < KR; ++k) {
-                    double2 w = Wt[(size_t)k * npairs + p];
-                    x0 = fma(w.x, f[k], x0);
-                    x1 = fma(w.y, f[k], x1);
-                }
-            } else {
-                for (int k = 0; k < C; ++k) {
-                    double2 w = Wt[(size_t)k * npairs + p];
-                    double fk = fsi[k * Tc + tt];
-                    x0 = fma(w.x, fk, x0);
-                    x1 = fma(w.y, fk, x1);
-                }
+            for (int k = 0; k < KR; ++k) {
+                const double2 w = Wt[(size_t)k * npairs + p];
+                x0 = fma(w.x, f[k], x0);
+                x1 = fma(w.y, f[k], x1);
             }
-            const bool v1 = (2 * p + 1) < n;      // the pad slot of an odd block
-            if (LOGPATH) {
-                logsum += log(x0);
-                if (v1) logsum += log(x1);
-            } else {
-                dg_acc(acc, x0);
-                dg_acc(acc, v1 ? x1 : 1.0);
-                if (((++it) & 127) == 0) dg_renorm(acc);
+        } else {
+            for (int k = 0; k < C; ++k) {
+                const double2 w = Wt[(size_t)k * npairs + p];
+                const double fk = fcol[k * Tc];
+                x0 = fma(w.x, fk, x0);
+                x1 = fma(w.y, fk, x1);
+            }
+        }
+        const bool v1 = (2 * p + 1) < n;              // the pad slot of an odd block
+        if (LOGPATH) {
+            logsum += log(x0);
+            if (v1) logsum += log(x1);
+        } else {
+            const double y1 = v1 ? x1 : 1.0;
+            const int h0 = __double2hiint(x0), h1 = __double2hiint(y1);
+            bad |= (((unsigned)(h0 - 0x00100000) >= 0x7fe00000u) || ((unsigned)(h1 - 0x00100000) >= 0x7fe00000u)) ? 1u : 0u;
+            e += (h0 >> 20) + (h1 >> 20) - 2046;
+            m0 *= __hiloint2double((h0 & 0x000fffff) | 0x3ff00000, __double2loint(x0));
+            m1 *= __hiloint2double((h1 & 0x000fffff) | 0x3ff00000, __double2loint(y1));
+            if (((++it) & 511) == 0) {                 // keep the running products in range
+                const int g0 = __double2hiint(m0), g1 = __double2hiint(m1);
+                e += (g0 >> 20) + (g1 >> 20) - 2046;
+                m0 = __hiloint2double((g0 & 0x000fffff) | 0x3ff00000, __double2loint(m0));
+                m1 = __hiloint2double((g1 & 0x000fffff) | 0x3ff00000, __double2loint(m1));
             }
         }
     }
 }
 
-template <bool LOGPATH>
-__device__ __forceinline__ void lik_dispatch(const double *Wc, int C, int Tc, const int *rel,
-                                             const int *ncnt, const double *fsi, int tid, int nthreads,
-                                             MantExp &acc, double &logsum) {
-    switch (C) {
-        case 1: lik_partial<1, LOGPATH>(Wc, C, Tc, rel, ncnt, fsi, tid, nthreads, acc, logsum); break;
-        case 2: lik_partial<2, LOGPATH>(Wc, C, Tc, rel, ncnt, fsi, tid, nthreads, acc, logsum); break;
-        case 3: lik_partial<3, LOGPATH>(Wc, C, Tc, rel, ncnt, fsi, tid, nthreads, acc, logsum); break;
-        case 4: lik_partial<4, LOGPATH>(Wc, C, Tc, rel, ncnt, fsi, tid, nthreads, acc, logsum); break;
-        case 5: lik_partial<5, LOGPATH>(Wc, C, Tc, rel, ncnt, fsi, tid, nthreads, acc, logsum); break;
-        case 6: lik_partial<6, LOGPATH>(Wc, C, Tc, rel, ncnt, fsi, tid, nthreads, acc, logsum); break;
-        case 7: lik_partial<7, LOGPATH>(Wc, C, Tc, rel, ncnt, fsi, tid, nthreads, acc, logsum); break;
-        case 8: lik_partial<8, LOGPATH>(Wc, C, Tc, rel, ncnt, fsi, tid, nthreads, acc, logsum); break;
-        default: lik_partial<0, LOGPATH>(Wc, C, Tc, rel, ncnt, fsi, tid, nthreads, acc, logsum); break;
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// block-wide state of one chain
-// ---------------------------------------------------------------------------------------
+// shapes and shared arrays of the chain a block is working on
 struct ChainCtx {
-    // shapes
-    int C, Tc, CT, CTm;          // CTm = (C-1)*Tc free latent values
+    int C, Tc, CT, CTm;               // CTm = (C-1)*Tc free latent values
     int tid, nthreads, lane, warp, nwarps;
-    // shared arrays
-    double *ynow, *ytry, *psinow, *psitry, *fsi, *ex, *pr, *qq, *zb;
-    double *kinv, *pfac, *lens, *ijs, *jcon, *sqs;
+    int nstate, S, NWL;               // state threads (multiple of 32), state warps, likelihood warps
+    double *ytry, *fsi, *ex, *gs, *pr, *qq, *zb;
+    double *kinv, *pfac, *ijs, *jcon, *sqs;
     double *red, *bc, *gw;
-    int *redi, *rel, *ncnt;
+    int *redi, *rel, *ncnt, *seg;
     unsigned *redb;
-    const double *Wc;            // shared or global
+    const double *Wc;                 // shared or global
     double prior_const;
 };
 
-// Full evaluation of the candidate in s.ytry: softmax / length reweighting
-// (model_GP.py:335-337), GP prior (:332, normal_pdf :89-91), proposal density (:330-331)
-// and read likelihood (:338-345).  Results land in bc[0]=prior, bc[1]=Q, bc[2]=lik.
-// Every thread of the block must call it.
-__device__ __forceinline__ void evaluate(ChainCtx &s, bool with_q DG_PROF_ARGS) {
-    const int C = s.C, Tc = s.Tc, CT = s.CT, tid = s.tid;
-    // phase 2: per (c,t): quadratic-form partials and exp
-    if (tid < CT) {
-        const int c = tid / Tc, t = tid - c * Tc;
-        const double *yc = s.ytry + c * Tc;
-        s.ex[tid] = exp(yc[t]);
-        if (c < C - 1) {
-            double r = 0.0;
-            for (int j = 0; j < Tc; ++j) r = fma(yc[j], s.kinv[j * Tc + t], r);
-            s.pr[tid] = r * yc[t];
-            if (with_q) {
-                const double *yn = s.ynow + c * Tc;
-                double dq = 0.0;
-                for (int j = 0; j < Tc; ++j) dq = fma(yn[j] - yc[j], s.kinv[j * Tc + t], dq);
-                s.qq[tid] = dq * (yn[t] - yc[t]);
-            }
-        }
+// Likelihood pass of one likelihood warp over its segments; leaves (mantissa, exponent,
+// bad) of the warp in red/redi/redb[wl].
+template <int KC>
+__device__ __forceinline__ void lik_warp_pass(const ChainCtx &s, int wl, int nseg) {
+    double m0 = 1.0, m1 = 1.0, dummy = 0.0;
+    int e = 0;
+    unsigned bad = 0u;
+    for (int sg = wl; sg < nseg; sg += s.NWL) {
+        const int tt = s.seg[3 * sg], first = s.seg[3 * sg + 1], stride = s.seg[3 * sg + 2];
+        const int r0 = s.rel[tt], npairs = (s.rel[tt + 1] - r0) >> 1;
+        const double2 *Wt = reinterpret_cast<const double2 *>(s.Wc + (size_t)s.C * r0);
+        lik_segment<KC, false>(Wt, npairs, s.ncnt[tt], s.C, s.fsi + tt, s.Tc, first + s.lane, stride, m0, m1, e, bad, dummy);
+        // a warp that walks many segments keeps its products in range
+        const int g0 = __double2hiint(m0), g1 = __double2hiint(m1);
+        e += (g0 >> 20) + (g1 >> 20) - 2046;
+        m0 = __hiloint2double((g0 & 0x000fffff) | 0x3ff00000, __double2loint(m0));
+        m1 = __hiloint2double((g1 & 0x000fffff) | 0x3ff00000, __double2loint(m1));
     }
-    __syncthreads();
-    DG_TICK(1);
-    // phase 3: per time point softmax + reweight; one thread sums prior and Q
-    if (tid < Tc) {
-        const int t = tid;
-        const double se = dg_np_sum(s.ex + t, C, Tc);
-        for (int k = 0; k < C; ++k) {
-            const double p = s.ex[k * Tc + t] / se;
-            s.psitry[k * Tc + t] = p;
-            s.fsi[k * Tc + t] = s.lens[t * C + k] * p;          // g_k, normalised below
-        }
-        const double sg = dg_np_sum(s.fsi + t, C, Tc);
-        for (int k = 0; k < C; ++k) s.fsi[k * Tc + t] = s.fsi[k * Tc + t] / sg;
-    } else if (tid == 32) {
-        // warp 1 (idle in phase 3 when Tc <= 32): prior and proposal density, c ascending
-        double prior = 0.0, Q = 0.0;
-        for (int c = 0; c < C - 1; ++c) {
-            double a = 0.0;
-            for (int t = 0; t < Tc; ++t) a += s.pr[c * Tc + t];
-            prior += s.prior_const - a / 2.0;
-            if (with_q) {
-                double b = 0.0;
-                for (int t = 0; t < Tc; ++t) b += s.qq[c * Tc + t];
-                Q += s.jcon[c] - (b * s.ijs[c]) / 2.0;
-            }
-        }
-        s.bc[0] = prior;
-        s.bc[1] = Q;
-    }
-    __syncthreads();
-    DG_TICK(2);
-    // phase 4: likelihood partials
-    MantExp acc;
-    acc.m = 1.0; acc.e = 0; acc.bad = 0u;
-    double dummy = 0.0;
-    lik_dispatch<false>(s.Wc, C, Tc, s.rel, s.ncnt, s.fsi, tid, s.nthreads, acc, dummy);
-    dg_renorm(acc);
+    double m = m0 * m1;                                     // < 4
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        acc.m *= __shfl_xor_sync(0xffffffffu, acc.m, off);
-        acc.e += __shfl_xor_sync(0xffffffffu, acc.e, off);
-        acc.bad |= __shfl_xor_sync(0xffffffffu, acc.bad, off);
+        m *= __shfl_xor_sync(0xffffffffu, m, off);          // < 4^32 = 2^64
+        e += __shfl_xor_sync(0xffffffffu, e, off);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, off);
     }
     if (s.lane == 0) {
-        dg_renorm(acc);
-        s.red[s.warp] = acc.m;
-        s.redi[s.warp] = acc.e;
-        s.redb[s.warp] = acc.bad;
+        const int g = __double2hiint(m);
+        s.red[wl] = __hiloint2double((g & 0x000fffff) | 0x3ff00000, __double2loint(m));
+        s.redi[wl] = e + (g >> 20) - 1023;
+        s.redb[wl] = bad;
     }
-    DG_TICK(3);
-    __syncthreads();
-    DG_TICK(4);
-    if (tid == 0) {
-        double m = 1.0;
-        long long e = 0;
-        unsigned bad = 0u;
-        for (int w = 0; w < s.nwarps; ++w) { m *= s.red[w]; e += s.redi[w]; bad |= s.redb[w]; }
-        s.bc[2] = fma((double)e, 0.693147180559945309417232121458, log(m));
-        s.bc[3] = bad ? 1.0 : 0.0;
+}
+
+// Slow path (some x_n is 0 / negative / non-finite): the same sum with real logarithms so
+// that -inf and NaN propagate like np.log(...).sum() does (model_GP.py:344).
+template <int KC>
+__device__ __noinline__ void lik_warp_pass_log(const double *Wc, const int *seg, const int *rel, const int *ncnt,
+                                               const double *fsi, double *red, int C, int Tc, int NWL, int lane,
+                                               int wl, int nseg) {
+    double m0 = 1.0, m1 = 1.0, ls = 0.0;
+    int e = 0;
+    unsigned bad = 0u;
+    for (int sg = wl; sg < nseg; sg += NWL) {
+        const int tt = seg[3 * sg], first = seg[3 * sg + 1], stride = seg[3 * sg + 2];
+        const int r0 = rel[tt], npairs = (rel[tt + 1] - r0) >> 1;
+        const double2 *Wt = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0);
+        lik_segment<KC, true>(Wt, npairs, ncnt[tt], C, fsi + tt, Tc, first + lane, stride, m0, m1, e, bad, ls);
     }
-    __syncthreads();
-    DG_TICK(5);
-    if (s.bc[3] != 0.0) {
-        // slow path: some read has a non-positive / non-finite likelihood term
-        double ls = 0.0;
-        lik_dispatch<true>(s.Wc, C, Tc, s.rel, s.ncnt, s.fsi, tid, s.nthreads, acc, ls);
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, off);
-        __syncthreads();                       // everyone has read bc[3]
-        if (s.lane == 0) s.red[s.warp] = ls;
-        __syncthreads();
-        if (tid == 0) {
-            double a = 0.0;
-            for (int w = 0; w < s.nwarps; ++w) a += s.red[w];
-            s.bc[2] = a;
-            s.bc[3] = 0.0;
-        }
-        __syncthreads();
-    }
+    for (int off = 16; off > 0; off >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, off);
+    if (lane == 0) red[wl] = ls;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -211,52 +154,50 @@ __device__ __forceinline__ void evaluate(ChainCtx &s, bool with_q DG_PROF_ARGS) 
 // Two-pass mean / population variance like np.mean / np.var.  Lanes walk columns
 // (coalesced), warps walk rows.  Returns 1 to every thread when all |Z| <= 2.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ int geweke_converged(ChainCtx &s, const TraceView &tv, int m) {
+__device__ __noinline__ int geweke_converged(double *gw, int CTm, int nwarps, int warp, int lane, TraceView tv, int m) {
     const int nA = (int)(0.1 * (double)m);
     const int iB = (int)(0.5 * (double)m);
     const int nB = m - iB;
     int ok = 1;
-    for (int c0 = 0; c0 < s.CTm; c0 += DG_GW_COLS) {
-        const int col = c0 + s.lane;
-        const bool act = col < s.CTm;
-        double *gA = s.gw, *gB = s.gw + s.nwarps * DG_GW_COLS;
-        // pass 1: sums
+    for (int c0 = 0; c0 < CTm; c0 += DG_GW_COLS) {
+        const int col = c0 + lane;
+        const bool act = col < CTm;
+        double *gA = gw, *gB = gw + nwarps * DG_GW_COLS;
         double sa = 0.0, sb = 0.0;
         if (act) {
-            for (int r = s.warp; r < nA; r += s.nwarps) sa += __ldcg(tv.row(r) + col);
-            for (int r = iB + s.warp; r < m; r += s.nwarps) sb += __ldcg(tv.row(r) + col);
+            for (int r = warp; r < nA; r += nwarps) sa += __ldcg(tv.row(r) + col);
+            for (int r = iB + warp; r < m; r += nwarps) sb += __ldcg(tv.row(r) + col);
         }
-        gA[s.warp * DG_GW_COLS + s.lane] = sa;
-        gB[s.warp * DG_GW_COLS + s.lane] = sb;
+        gA[warp * DG_GW_COLS + lane] = sa;
+        gB[warp * DG_GW_COLS + lane] = sb;
         __syncthreads();
         double meanA = 0.0, meanB = 0.0;
-        for (int w = 0; w < s.nwarps; ++w) {
-            meanA += gA[w * DG_GW_COLS + s.lane];
-            meanB += gB[w * DG_GW_COLS + s.lane];
+        for (int w = 0; w < nwarps; ++w) {
+            meanA += gA[w * DG_GW_COLS + lane];
+            meanB += gB[w * DG_GW_COLS + lane];
         }
         meanA /= (double)nA;
         meanB /= (double)nB;
         __syncthreads();
-        // pass 2: centred sums of squares
         double qa = 0.0, qb = 0.0;
         if (act) {
-            for (int r = s.warp; r < nA; r += s.nwarps) {
-                double d = __ldcg(tv.row(r) + col) - meanA;
+            for (int r = warp; r < nA; r += nwarps) {
+                const double d = __ldcg(tv.row(r) + col) - meanA;
                 qa = fma(d, d, qa);
             }
-            for (int r = iB + s.warp; r < m; r += s.nwarps) {
-                double d = __ldcg(tv.row(r) + col) - meanB;
+            for (int r = iB + warp; r < m; r += nwarps) {
+                const double d = __ldcg(tv.row(r) + col) - meanB;
                 qb = fma(d, d, qb);
             }
         }
-        gA[s.warp * DG_GW_COLS + s.lane] = qa;
-        gB[s.warp * DG_GW_COLS + s.lane] = qb;
+        gA[warp * DG_GW_COLS + lane] = qa;
+        gB[warp * DG_GW_COLS + lane] = qb;
         __syncthreads();
-        if (s.warp == 0 && act) {
+        if (warp == 0 && act) {
             double va = 0.0, vb = 0.0;
-            for (int w = 0; w < s.nwarps; ++w) {
-                va += gA[w * DG_GW_COLS + s.lane];
-                vb += gB[w * DG_GW_COLS + s.lane];
+            for (int w = 0; w < nwarps; ++w) {
+                va += gA[w * DG_GW_COLS + lane];
+                vb += gB[w * DG_GW_COLS + lane];
             }
             va /= (double)nA;
             vb /= (double)nB;
@@ -270,31 +211,59 @@ __device__ __forceinline__ int geweke_converged(ChainCtx &s, const TraceView &tv
     return __syncthreads_and(ok);
 }
 
+// Which likelihood warp reads which slice: segment = (time point, first pair, stride).
+// Warps are dealt to time points in proportion to their read pairs; with fewer warps
+// than time points every time point is one segment and warps take several.
+__device__ __noinline__ int build_segments(int *seg, const int *rel, int Tc, int NWL) {
+    if (Tc >= NWL) {
+        for (int t = 0; t < Tc; ++t) { seg[3 * t] = t; seg[3 * t + 1] = 0; seg[3 * t + 2] = 32; }
+        return Tc;
+    }
+    int nw[DG_MAXT];
+    for (int t = 0; t < Tc; ++t) nw[t] = 1;
+    for (int w = Tc; w < NWL; ++w) {
+        int best = 0;
+        double load = -1.0;
+        for (int t = 0; t < Tc; ++t) {
+            const double l = (double)(rel[t + 1] - rel[t]) / (double)nw[t];
+            if (l > load) { load = l; best = t; }
+        }
+        ++nw[best];
+    }
+    int k = 0;
+    for (int t = 0; t < Tc; ++t)
+        for (int j = 0; j < nw[t]; ++j) { seg[3 * k] = t; seg[3 * k + 1] = 32 * j; seg[3 * k + 2] = 32 * nw[t]; ++k; }
+    return k;
+}
+
 // ---------------------------------------------------------------------------------------
 // one chain, up to n_steps steps.  `slot` indexes the host stream blocks.
 // ---------------------------------------------------------------------------------------
-template <bool W_IN_SMEM>
+template <int KC, bool W_IN_SMEM>
 __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArgs &sa, int chain,
                           int slot, int n_steps, double *smem, int use_tma) {
     ChainCtx s;
     s.tid = threadIdx.x; s.nthreads = blockDim.x;
-    s.lane = s.tid & 31; s.warp = s.tid >> 5; s.nwarps = (s.nthreads + 31) >> 5;
+    s.lane = s.tid & 31; s.warp = s.tid >> 5; s.nwarps = s.nthreads >> 5;
     if (ct.state[chain] != 0) return;                    // already finished (block-uniform)
 
     const int g = ct.gene[chain], t0 = ct.t0[chain];
     const int C = gt.C[g], Tc = ct.Tc[chain], T = gt.T;
     s.C = C; s.Tc = Tc; s.CT = C * Tc; s.CTm = (C - 1) * Tc;
+    s.S = (s.CT + 31) >> 5; s.nstate = s.S << 5; s.NWL = s.nwarps - s.S;
     const SmLayout L = dg_layout(C, Tc, s.nwarps);
-    s.ynow = smem + L.ynow; s.ytry = smem + L.ytry; s.psinow = smem + L.psinow;
-    s.psitry = smem + L.psitry; s.fsi = smem + L.fsi; s.ex = smem + L.ex; s.pr = smem + L.pr;
-    s.qq = smem + L.qq; s.zb = smem + L.zb; s.kinv = smem + L.kinv; s.pfac = smem + L.pfac;
-    s.lens = smem + L.lens; s.ijs = smem + L.ijs; s.jcon = smem + L.jcon; s.sqs = smem + L.sqs;
-    s.red = smem + L.red; s.redi = reinterpret_cast<int *>(smem + L.redi);
+    s.ytry = smem + L.ytry; s.fsi = smem + L.fsi; s.ex = smem + L.ex; s.gs = smem + L.gs;
+    s.pr = smem + L.pr; s.qq = smem + L.qq; s.zb = smem + L.zb; s.kinv = smem + L.kinv;
+    s.pfac = smem + L.pfac; s.ijs = smem + L.ijs; s.jcon = smem + L.jcon;
+    s.sqs = smem + L.sqs; s.red = smem + L.red; s.redi = reinterpret_cast<int *>(smem + L.redi);
     s.redb = reinterpret_cast<unsigned *>(smem + L.redb); s.bc = smem + L.bc; s.gw = smem + L.gw;
     s.rel = reinterpret_cast<int *>(smem + L.rel); s.ncnt = s.rel + (Tc + 1);
+    s.seg = reinterpret_cast<int *>(smem + L.seg);
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + L.mbar);
     double *Wsm = smem + L.w;
     s.prior_const = ct.prior_const[chain];
+    const bool is_state = s.tid < s.nstate;
+    const int wl = s.warp - s.S;                          // likelihood-warp index (>= 0 for those)
 
     const int32_t *roff = gt.roff + (size_t)g * (T + 1) + t0;
     const int r_first = roff[0];
@@ -316,7 +285,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                 const uint32_t kChunk = 32768u;
                 size_t done = 0;
                 while (done < wbytes) {
-                    uint32_t sz = (uint32_t)((wbytes - done) < kChunk ? (wbytes - done) : kChunk);
+                    const uint32_t sz = (uint32_t)((wbytes - done) < kChunk ? (wbytes - done) : kChunk);
                     asm volatile(
                         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                         ::"r"(dg_smem_u32(reinterpret_cast<char *>(Wsm) + done)),
@@ -351,39 +320,37 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             s.sqs[i] = sqrt(js[i]);
             s.jcon[i] = jc[i];
         }
-        const double *lens = gt.len + gt.lenoff[g] + (size_t)t0 * C;
-        for (int i = s.tid; i < Tc * C; i += s.nthreads) s.lens[i] = lens[i];
     }
-#ifdef DG_PROFILE
-    long long dg_prof[10];
-    long long dg_t0 = 0;
-    long long *dg_prof_out = reinterpret_cast<long long *>(const_cast<double *>(sa.prof));
-#endif
     const int M = ct.M[chain], initial = ct.initial[chain], gap = ct.gap[chain];
     int m = ct.m_next[chain];
-    int cnt = ct.cnt[chain];
-    int flags = ct.flags[chain];
     double *st = ct.st + ct.st_off[chain];
-    double P_now = 0.0, L_now = 0.0;                      // live in thread 0
     const int rowlen = 2 * s.CT + 2;
     int64_t *ptab = ct.ptab + ct.ptab_off[chain];
     const int pshift = ct.pshift[chain];
     const int pmask = (1 << pshift) - 1;
     TraceView tv;
     tv.pool = ct.trace; tv.tab = ptab; tv.shift = pshift; tv.rowlen = rowlen;
-    double *page = nullptr;                               // base of the page holding row m
     const int64_t sid = ct.stream_id ? ct.stream_id[chain] : (int64_t)chain;
+    const bool dev_stream = sa.mode != 0;
 
-    if (m == 0) {
-        const double *y0 = ct.y0_off[chain] >= 0 ? ct.pool + ct.y0_off[chain] : nullptr;
-        if (s.tid < s.CT) s.ytry[s.tid] = y0 ? y0[s.tid] : 0.0;          // Y_now = Ymean (:275)
-    } else {
-        if (s.tid < s.CT) { s.ynow[s.tid] = st[s.tid]; s.psinow[s.tid] = st[s.CT + s.tid]; }
-        if (s.tid == 0) { P_now = st[2 * s.CT]; L_now = st[2 * s.CT + 1]; }
-    }
+    // per state thread: its latent value (c, t); current state lives in registers
+    const int si = s.tid;                                 // state index = c*Tc + t
+    const bool s_act = is_state && si < s.CT;             // owns a value
+    const bool s_free = is_state && si < s.CTm;           // value is sampled (c < C-1)
+    const int sc = s_act ? si / Tc : 0;
+    const int stt = s_act ? si - sc * Tc : 0;
+    double y_now = 0.0, psi_now = 0.0;
+    double P_now = 0.0, L_now = 0.0;                      // thread 0
+    int cnt = 0, flags = 0;
+    if (s.tid == 0) { cnt = ct.cnt[chain]; flags = ct.flags[chain]; }
+    const double len_own = s_act ? gt.len[gt.lenoff[g] + (size_t)(t0 + stt) * C + sc] : 0.0;
+
+    __syncthreads();                                      // rel / ncnt visible
+    if (s.tid == 0) s.bc[6] = (double)build_segments(s.seg, s.rel, Tc, s.NWL);
+    if (m > 0 && s_act) { y_now = st[si]; psi_now = st[s.CT + si]; }
+    if (m > 0 && s.tid == 0) { P_now = st[2 * s.CT]; L_now = st[2 * s.CT + 1]; }
     if (W_IN_SMEM && use_tma && wbytes > 0) {
-        // wait for the bulk copy (phase 0)
-        uint32_t ok = 0;
+        uint32_t ok = 0;                                  // wait for the bulk copy (phase 0)
         while (!ok) {
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
@@ -393,152 +360,255 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         }
     }
     __syncthreads();
+    const int nseg = (int)s.bc[6];
 
-    if (m == 0) {
-        // initial state: P_now / L_now of the start value (model_GP.py:278-292)
-        evaluate(s, false DG_PROF_PASS);
-        if (s.tid < s.CT) {
-            s.ynow[s.tid] = s.ytry[s.tid];
-            s.psinow[s.tid] = s.psitry[s.tid];
-        }
-        if (s.tid == 0) {
-            L_now = s.bc[2];
-            P_now = s.bc[0] + s.bc[2];
-            if (!isfinite(P_now)) flags |= 1;
-        }
-        __syncthreads();
-        if (s.tid >= s.CTm && s.tid < s.CT) s.ytry[s.tid] = 0.0;          // Y_try[C-1,:] stays 0 (:295)
-        __syncthreads();
-    }
-
-    int state = 0, m_ret = 0;
-    // ---- stream set-up ---------------------------------------------------------------------
     const int m_start = m;
     const int m_end = (m_start + n_steps < M) ? (m_start + n_steps) : M;
+    int state = 0, m_ret = 0;
+    double *page = nullptr;                               // state threads: page of the row being written
+
+    // ---- stream set-up ---------------------------------------------------------------------
     const double *dblk = nullptr, *ublk = nullptr;
-    double d_next = 0.0, u_next = 0.0;
-    if (sa.mode == 0) {
+    double d_next = 0.0, lu_next = 0.0;
+    if (!dev_stream) {
         dblk = sa.delta + sa.delta_off[slot];
         ublk = sa.u + sa.u_off[slot];
         if (m < m_end) {
-            if (s.tid < s.CTm) d_next = dblk[s.tid];
-            if (s.tid == 0) u_next = ublk[0];
+            if (s_free) d_next = dblk[si];
+            if (s.tid == 0) lu_next = log(ublk[0]);
         }
-    } else if (m < m_end) {
-        if (s.tid < s.CTm) s.zb[(m & 1) * s.CT + s.tid] = dg_normal(sa.seed, sid, (uint32_t)m, (uint32_t)s.tid);
-        if (s.tid == 0) u_next = dg_uniform(sa.seed, sid, (uint32_t)m);
+    } else {
+        // z and log(u) of the first two steps (later ones are produced two steps ahead by
+        // the likelihood warps); slot CT-1 of a z buffer holds log(u)
+        for (int k = 0; k < 2; ++k) {
+            const int mm = m + k;
+            for (int i = s.tid; i < s.CTm; i += s.nthreads)
+                s.zb[(mm & 1) * s.CT + i] = dg_normal(sa.seed, sid, (uint32_t)mm, (uint32_t)i);
+            if (s.tid == s.nthreads - 1) s.zb[(mm & 1) * s.CT + s.CT - 1] = log(dg_uniform(sa.seed, sid, (uint32_t)mm));
+        }
         __syncthreads();
     }
-
 #ifdef DG_PROFILE
-    dg_t0 = clock64();
+    long long dg_prof[10];
+    long long dg_t0 = clock64();
     for (int i = 0; i < 10; ++i) dg_prof[i] = 0;
 #endif
-    for (; m < m_end; ++m) {
-        // trace page of row m (allocated on first touch; the first page always exists)
-        if (page == nullptr || (m & pmask) == 0) {
+
+    // it == -1: evaluate the start value (model_GP.py:275-292) with the same machinery as a
+    // step (always "accepted", no trace row), then steps m .. m_end-1
+    for (int it = (m == 0 ? -1 : m); it < m_end; ++it) {
+        const bool init = it < 0;
+        const int mcur = init ? 0 : it;
+        double y_try = 0.0, e_try = 1.0, g_own = 0.0, psi_try = 0.0, lu_cur = 0.0;
+        // ================= S phase (state warps): proposal -> f =================
+        if (is_state) {
+            if (init) {
+                const double *y0 = ct.y0_off[chain] >= 0 ? ct.pool + ct.y0_off[chain] : nullptr;
+                if (s_act) y_try = y0 ? y0[si] : 0.0;                       // Y_now = Ymean (:275)
+            } else if (s_free) {
+                double d;
+                if (!dev_stream) {
+                    d = d_next;
+                } else {
+                    const double *z = s.zb + (mcur & 1) * s.CT + sc * Tc;
+                    double a = 0.0;
+                    for (int j = 0; j < Tc; ++j) a = fma(z[j], s.pfac[j * Tc + stt], a);
+                    d = s.sqs[sc] * a;
+                }
+                y_try = d + y_now;                                           // (:329) numpy adds the mean last
+            }                                                                // else Y_try[C-1,:] stays 0 (:295)
+            if (s.tid == 0 && !init) lu_cur = dev_stream ? s.zb[(mcur & 1) * s.CT + s.CT - 1] : lu_next;
+            if (s_act) {
+                e_try = exp(y_try);
+                g_own = len_own * e_try;
+                s.ytry[si] = y_try;
+                s.ex[si] = e_try;
+                s.gs[si] = g_own;
+            }
+            bar_state(s.nstate);
+            if (s_act) {
+                // fsi = len*psi / sum(len*psi) with psi = e/sum(e): the common 1/sum(e) cancels
+                // (model_GP.py:335-337; one division on the critical path instead of two)
+                const double sg = dg_np_sum(s.gs + stt, C, Tc);
+                s.fsi[si] = g_own / sg;
+            }
+        }
+        __syncthreads();                                                     // B1: f ready
+        DG_TICK(0);
+        // ================= likelihood warps || rest of the serial part =================
+        if (!is_state) {
+            lik_warp_pass<KC>(s, wl, nseg);
+        } else {
+            if (!dev_stream && !init && mcur + 1 < m_end) {                  // host stream: prefetch
+                if (s_free) d_next = dblk[(size_t)(mcur + 1 - m_start) * s.CTm + si];
+                if (s.tid == 0) lu_next = log(ublk[mcur + 1 - m_start]);
+            }
+            if (s_act) {
+                const double se = dg_np_sum(s.ex + stt, C, Tc);
+                psi_try = e_try / se;                                        // (:335)
+            }
+            // GP prior (:332) and proposal density (:330-331): x K^-1 x as (x K^-1)[t] * x[t]
+            if (s_free) {
+                const double *yc = s.ytry + sc * Tc;
+                double r = 0.0;
+                for (int j = 0; j < Tc; ++j) r = fma(yc[j], s.kinv[j * Tc + stt], r);
+                s.pr[si] = r * y_try;
+                s.qq[si] = y_now - y_try;                                    // d = Y_now - Y_try
+            }
+            bar_state(s.nstate);
+            double qpart = 0.0;
+            if (s_free && !init) {
+                const double *dc = s.qq + sc * Tc;
+                double dq = 0.0;
+                for (int j = 0; j < Tc; ++j) dq = fma(dc[j], s.kinv[j * Tc + stt], dq);
+                qpart = dq * (y_now - y_try);
+            }
+            bar_state(s.nstate);                                             // everyone has read qq
+            if (s_free) s.qq[si] = qpart;
+            bar_state(s.nstate);
+            if (s.tid < C - 1) {
+                const int c = s.tid;
+                double a = 0.0, b = 0.0;
+                for (int t = 0; t < Tc; ++t) { a += s.pr[c * Tc + t]; b += s.qq[c * Tc + t]; }
+                s.pr[c * Tc] = s.prior_const - a / 2.0;
+                s.qq[c * Tc] = s.jcon[c] - (b * s.ijs[c]) / 2.0;
+            }
+            bar_state(s.nstate);
             if (s.tid == 0) {
-                long long e = __ldcg(ptab + (m >> pshift));
-                if (e < 0) {
-                    const unsigned long long need = (unsigned long long)rowlen << pshift;
-                    const unsigned long long off = atomicAdd(ct.pool_head, need);
-                    if (off + need <= (unsigned long long)ct.pool_cap) {
-                        e = (long long)off;
-                        ptab[m >> pshift] = e;
+                double prior = 0.0, Q = 0.0;                                 // c ascending (:312-332)
+                for (int c = 0; c < C - 1; ++c) {
+                    prior += s.pr[c * Tc];
+                    if (!init) Q += s.qq[c * Tc];
+                }
+                s.bc[0] = prior;
+                s.bc[1] = Q;
+            }
+        }
+        DG_TICK(1);
+        __syncthreads();                                                     // B2: partial likelihoods ready
+        DG_TICK(2);
+        // ================= decision (warp 0; thread 0 decides) =================
+        bool redo = false;
+        do {
+            if (s.warp == 0) {
+                double lik;
+                unsigned bad = 0u;
+                if (!redo) {
+                    double mm = s.lane < s.NWL ? s.red[s.lane] : 1.0;
+                    int ee = s.lane < s.NWL ? s.redi[s.lane] : 0;
+                    bad = s.lane < s.NWL ? s.redb[s.lane] : 0u;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        mm *= __shfl_xor_sync(0xffffffffu, mm, off);         // < 2^32
+                        ee += __shfl_xor_sync(0xffffffffu, ee, off);
+                        bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+                    }
+                    lik = fma((double)ee, 0.693147180559945309417232121458, log(mm));
+                } else {
+                    lik = 0.0;
+                    for (int w = 0; w < s.NWL; ++w) lik += s.red[w];
+                }
+                if (s.lane == 0) {
+                    s.bc[3] = bad ? 1.0 : 0.0;
+                    if (!bad) {
+                        const double Q = s.bc[1];
+                        const double P_try = s.bc[0] + lik;
+                        bool acc;
+                        if (init) {
+                            acc = true;                                      // P_now / L_now of the start value
+                        } else {
+                            // alpha = exp(min(a, 0)), accept iff u < alpha (:348-351): tested in the
+                            // log domain, log(u) having been taken off the critical path
+                            const double a = ((P_try + Q) - P_now) - Q;
+                            acc = (a >= 0.0) || (lu_cur < a);                // NaN a: both false
+                            if (acc) ++cnt;
+                        }
+                        if (!isfinite(P_try)) flags |= 1;
+                        if (acc) { P_now = P_try; L_now = lik; }
+                        // trace page of row m (allocated on first touch; the first page always exists)
+                        long long pg = 0;
+                        if (!init && (page == nullptr || (mcur & pmask) == 0)) {
+                            pg = __ldcg(ptab + (mcur >> pshift));
+                            if (pg < 0) {
+                                const unsigned long long need = (unsigned long long)rowlen << pshift;
+                                const unsigned long long off = atomicAdd(ct.pool_head, need);
+                                if (off + need <= (unsigned long long)ct.pool_cap) {
+                                    pg = (long long)off;
+                                    ptab[mcur >> pshift] = pg;
+                                }
+                            }
+                        }
+                        s.bc[4] = acc ? 1.0 : 0.0;
+                        s.bc[5] = __longlong_as_double(pg);
                     }
                 }
-                s.bc[5] = __longlong_as_double(e);
             }
+            __syncthreads();                                                 // B3: decision (or redo request)
+            redo = s.bc[3] != 0.0;
+            if (redo) {                                                      // rare: some x_n was not a positive normal
+                if (!is_state) lik_warp_pass_log<KC>(s.Wc, s.seg, s.rel, s.ncnt, s.fsi, s.red, C, Tc, s.NWL, s.lane, wl, nseg);
+                __syncthreads();
+            }
+        } while (redo);
+        DG_TICK(3);
+        // ================= update + trace row (state warps) || stream production (others) ======
+        const long long pg_new = __double_as_longlong(s.bc[5]);
+        if (is_state) {
+            if (s.bc[4] != 0.0 && s_act) { y_now = y_try; psi_now = psi_try; }
+            if (!init) {
+                if (page == nullptr || (mcur & pmask) == 0) page = pg_new >= 0 ? ct.trace + pg_new : nullptr;
+                if (page != nullptr) {
+                    double *row = page + (size_t)(mcur & pmask) * rowlen;
+                    if (s_act) {
+                        row[si] = psi_now;                                   // Psi_all[m]  (:365)
+                        row[s.CT + si] = y_now;                              // Y_all[m]    (:364)
+                    }
+                    if (s.tid == 0) {
+                        row[2 * s.CT] = P_now;                               // Pro_all[m]  (:362)
+                        row[2 * s.CT + 1] = L_now;                           // Lik_all[m]  (:363)
+                    }
+                }
+            }
+        } else if (dev_stream && !init && mcur + 2 < m_end) {
+            const int mm = mcur + 2;                                         // buffer released by step m
+            for (int i = s.tid - s.nstate; i < s.CTm; i += s.nthreads - s.nstate)
+                s.zb[(mm & 1) * s.CT + i] = dg_normal(sa.seed, sid, (uint32_t)mm, (uint32_t)i);
+            if (s.tid == s.nthreads - 1) s.zb[(mm & 1) * s.CT + s.CT - 1] = log(dg_uniform(sa.seed, sid, (uint32_t)mm));
+        }
+        if (init) continue;
+        if (pg_new < 0) {                                                    // trace pool exhausted (uniform)
+            state = DICEGP_CHAIN_NOMEM_;
+            m_ret = mcur - 1;
+            m = mcur;
+            break;
+        }
+        m = mcur + 1;
+        // convergence diagnostics (:369-391); rows [0, m) exclude the one just written
+        if (mcur >= initial && (mcur % gap) == 0) {
             __syncthreads();
-            const long long e = __double_as_longlong(s.bc[5]);
-            if (e < 0) {                                  // trace pool exhausted
-                state = DICEGP_CHAIN_NOMEM_;
-                m_ret = m - 1;
-                break;
-            }
-            page = ct.trace + e;
-        }
-        // phase 1: proposal Y_try = delta + Y_now (model_GP.py:329; numpy adds the mean last)
-        double u_cur = u_next;
-        if (s.tid < s.CTm) {
-            double d;
-            if (sa.mode == 0) {
-                d = d_next;
-            } else {
-                const int c = s.tid / Tc, t = s.tid - c * Tc;
-                const double *z = s.zb + (m & 1) * s.CT + c * Tc;
-                double a = 0.0;
-                for (int j = 0; j < Tc; ++j) a = fma(z[j], s.pfac[j * Tc + t], a);
-                d = s.sqs[c] * a;
-            }
-            s.ytry[s.tid] = d + s.ynow[s.tid];
-        }
-        // prefetch the next step's stream entries (off the critical path)
-        if (m + 1 < m_end) {
-            if (sa.mode == 0) {
-                if (s.tid < s.CTm) d_next = dblk[(size_t)(m + 1 - m_start) * s.CTm + s.tid];
-                if (s.tid == 0) u_next = ublk[m + 1 - m_start];
-            } else {
-                if (s.tid < s.CTm)
-                    s.zb[((m + 1) & 1) * s.CT + s.tid] = dg_normal(sa.seed, sid, (uint32_t)(m + 1), (uint32_t)s.tid);
-                if (s.tid == 0) u_next = dg_uniform(sa.seed, sid, (uint32_t)(m + 1));
-            }
-        }
-        __syncthreads();
-        DG_TICK(0);
-        evaluate(s, true DG_PROF_PASS);
-        // MH decision (model_GP.py:348-360), thread 0
-        if (s.tid == 0) {
-            const double lik = s.bc[2], Q = s.bc[1];
-            const double P_try = s.bc[0] + lik;
-            const double a = ((P_try + Q) - P_now) - Q;
-            const double amin = (0.0 < a) ? 0.0 : a;          // Python min(a, 0): NaN stays NaN
-            const double alpha = exp(amin);
-            const bool acc = u_cur < alpha;
-            if (!isfinite(P_try)) flags |= 1;
-            if (acc) { P_now = P_try; L_now = lik; ++cnt; }
-            s.bc[4] = acc ? 1.0 : 0.0;
-            double *row = page + (size_t)(m & pmask) * rowlen;
-            row[2 * s.CT] = P_now;                             // Pro_all[m]  (:362)
-            row[2 * s.CT + 1] = L_now;                         // Lik_all[m]  (:363)
-        }
-        __syncthreads();
-        DG_TICK(6);
-        if (s.tid < s.CT) {
-            if (s.bc[4] != 0.0) {
-                s.ynow[s.tid] = s.ytry[s.tid];
-                s.psinow[s.tid] = s.psitry[s.tid];
-            }
-            double *row = page + (size_t)(m & pmask) * rowlen;
-            row[s.tid] = s.psinow[s.tid];                      // Psi_all[m]  (:365)
-            row[s.CT + s.tid] = s.ynow[s.tid];                 // Y_all[m]    (:364)
-        }
-        // convergence diagnostics (:369-391); the rows [0, m) exclude the one just written
-        if (m >= initial && (m % gap) == 0) {
-            __syncthreads();
-            DG_TICK(7);
-            if (geweke_converged(s, tv, m)) {
+            DG_TICK(4);
+            const int conv = geweke_converged(s.gw, s.CTm, s.nwarps, s.warp, s.lane, tv, mcur);
+            DG_TICK(5);
+            if (conv) {
                 state = DICEGP_CHAIN_CONVERGED_;
-                m_ret = m;
-                ++m;
+                m_ret = mcur;
                 break;
             }
-            DG_TICK(8);
         }
-        __syncthreads();
-        DG_TICK(7);
+        DG_TICK(4);
     }
 #ifdef DG_PROFILE
-    if (threadIdx.x == 0 && dg_prof_out) {
-        for (int i = 0; i < 10; ++i) atomicAdd((unsigned long long *)dg_prof_out + i, (unsigned long long)dg_prof[i]);
-        atomicAdd((unsigned long long *)dg_prof_out + 10, (unsigned long long)(m - m_start));
+    if (threadIdx.x == 0 && sa.prof) {
+        unsigned long long *o = reinterpret_cast<unsigned long long *>(const_cast<double *>(sa.prof));
+        for (int i = 0; i < 10; ++i) atomicAdd(o + i, (unsigned long long)dg_prof[i]);
+        atomicAdd(o + 10, (unsigned long long)(m - m_start));
     }
 #endif
     if (state == 0 && m >= M) { state = DICEGP_CHAIN_EXHAUSTED_; m_ret = M - 1; }
 
     // ---- save state ------------------------------------------------------------------------
     __syncthreads();
-    if (s.tid < s.CT) { st[s.tid] = s.ynow[s.tid]; st[s.CT + s.tid] = s.psinow[s.tid]; }
+    if (s_act) { st[si] = y_now; st[s.CT + si] = psi_now; }
     if (s.tid == 0) {
         st[2 * s.CT] = P_now; st[2 * s.CT + 1] = L_now;
         ct.m_next[chain] = m;

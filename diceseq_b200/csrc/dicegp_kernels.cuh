@@ -85,11 +85,10 @@ struct TraceView {
 // ---------------------------------------------------------------------------------------
 struct SmLayout {
     // offsets in doubles from the start of dynamic shared memory
-    int ynow, ytry, psinow, psitry, fsi, ex, pr, qq, zb;      // CT each (zb: 2*CT)
+    int ytry, fsi, ex, gs, pr, qq, zb;                         // CT each (zb: 2*CT)
     int kinv, pfac;                                            // Tc*Tc each
-    int lens;                                                  // Tc*C
     int ijs, jcon, sqs;                                        // C each
-    int red, redi, redb, bc, gw, rel, mbar;                    // scratch
+    int red, redi, redb, bc, gw, rel, seg, mbar;               // scratch
     int w;                                                     // W (resident classes)
     int total;                                                 // doubles without W
 };
@@ -97,18 +96,17 @@ struct SmLayout {
 __host__ __device__ inline SmLayout dg_layout(int C, int Tc, int nwarps) {
     SmLayout L;
     int CT = C * Tc, TT = Tc * Tc, o = 0;
-    L.ynow = o; o += CT;  L.ytry = o; o += CT;  L.psinow = o; o += CT;  L.psitry = o; o += CT;
-    L.fsi = o; o += CT;   L.ex = o; o += CT;    L.pr = o; o += CT;      L.qq = o; o += CT;
-    L.zb = o; o += 2 * CT;
+    L.ytry = o; o += CT;  L.fsi = o; o += CT;  L.ex = o; o += CT;  L.gs = o; o += CT;
+    L.pr = o; o += CT;    L.qq = o; o += CT;   L.zb = o; o += 2 * CT;
     L.kinv = o; o += TT;  L.pfac = o; o += TT;
-    L.lens = o; o += CT;
-    L.ijs = o; o += C;    L.jcon = o; o += C;   L.sqs = o; o += C;
+    L.ijs = o; o += C;    L.jcon = o; o += C;  L.sqs = o; o += C;
     L.red = o; o += DG_MAXWARPS;
     L.redi = o; o += DG_MAXWARPS / 2;          // ints
     L.redb = o; o += DG_MAXWARPS / 2;          // unsigned
     L.bc = o; o += 8;
     L.gw = o; o += 2 * nwarps * DG_GW_COLS;
-    L.rel = o; o += (2 * (Tc + 1) + 1) / 2 + 1; // ints: rel roff[Tc+1], ncnt[Tc]
+    L.rel = o; o += Tc + 2;                    // ints: rel roff[Tc+1], ncnt[Tc]
+    L.seg = o; o += (3 * DG_MAXWARPS + 1) / 2 + 1;   // ints: up to 32 segments x (tt, first, stride)
     L.mbar = o; o += 2;
     o = (o + 15) & ~15;                         // 128-byte align W
     L.w = o;
