@@ -63,6 +63,10 @@ class BatchResult:
         return len(self.n_iso)
 
     def __getitem__(self, g):
+        if isinstance(g, slice):
+            return [self[i] for i in range(*g.indices(len(self)))]
+        if g < 0:
+            g += len(self)
         if g < 0 or g >= len(self):
             raise IndexError(g)
         r = GeneResult()

@@ -29,25 +29,27 @@ constexpr int DICEGP_CHAIN_NOMEM_ = 3;
 #ifndef DG_LB_THREADS
 #define DG_LB_THREADS DG_MAXTHREADS      // 1024 threads/SM -> 64 registers per thread
 #endif
+#ifndef DG_SPEC_DEPTH
+#define DG_SPEC_DEPTH 2                  // MH steps decided per pass over W (speculation tree depth)
+#endif
 template <int KC, bool W_IN_SMEM>
 __global__ void __launch_bounds__(DG_LB_THREADS, 1)
 dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__restrict__ ids, int n_ids,
                     int n_steps, int use_tma, int *queue) {
     extern __shared__ __align__(128) double dg_smem[];
-    if (queue == nullptr) {
-        const int slot = blockIdx.x;
-        if (slot < n_ids) dg::run_chain<KC, W_IN_SMEM>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma);
-        return;
-    }
     __shared__ int next_slot;
+    int slot = blockIdx.x;
     while (true) {
-        if (threadIdx.x == 0) next_slot = atomicAdd(queue, 1);
-        __syncthreads();
-        const int slot = next_slot;
-        __syncthreads();
+        if (queue != nullptr) {
+            if (threadIdx.x == 0) next_slot = atomicAdd(queue, 1);
+            __syncthreads();
+            slot = next_slot;
+            __syncthreads();
+        }
         if (slot >= n_ids) break;
-        dg::run_chain<KC, W_IN_SMEM>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma);
+        dg::run_chain<KC, W_IN_SMEM, DG_SPEC_DEPTH>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma);
         __syncthreads();
+        if (queue == nullptr) break;
     }
 }
 
@@ -421,7 +423,7 @@ void launch_classes(const dicegp_ctx *c, LaunchClass out[kTiers]) {
 }
 
 size_t fixed_smem_bytes(int C, int Tc, int threads) {
-    return (size_t)dg_layout(C, Tc, (threads + 31) / 32).total * sizeof(double);
+    return (size_t)dg_layout(C, Tc, (threads + 31) / 32, DG_SPEC_DEPTH).total * sizeof(double);
 }
 
 int64_t chain_reads(const dicegp_ctx *c, int chain) {
@@ -438,8 +440,12 @@ int64_t chain_wbytes(const dicegp_ctx *c, int chain) {
 
 inline int kind_of(int C) { return (C >= 2 && C <= 8) ? C - 1 : 0; }
 
-// threads a chain needs at least: its state warps plus one likelihood warp
-inline int min_threads(int C, int Tc) { return ((C * Tc + 31) / 32) * 32 + 32; }
+// threads a chain needs at least: its state warps (one lane per candidate node and latent
+// value) plus one likelihood warp
+inline int min_threads(int C, int Tc) {
+    const int J = (1 << DG_SPEC_DEPTH) - 1;
+    return ((J * C * Tc + 31) / 32) * 32 + 32;
+}
 
 int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain) {
     const dicegp_chain_desc &d = c->hdesc[chain];
@@ -604,11 +610,11 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     {
         unsigned long long h[16];
         DG_CUDA(c, cudaMemcpy(h, c->dprof.p, sizeof h, cudaMemcpyDeviceToHost));
-        const char *nm[9] = {"propose", "exp+quad", "softmax", "lik", "lik-wait", "reduce", "decide", "update", "geweke"};
+        const char *nm[9] = {"S", "window", "B2wait", "decide", "update", "geweke", "-", "-", "-"};
         double n = (double)std::max<unsigned long long>(h[10], 1);
         fprintf(stderr, "[dg_prof] steps=%llu cycles/step:", h[10]);
         double tot = 0;
-        for (int i = 0; i < 9; ++i) { fprintf(stderr, " %s=%.0f", nm[i], h[i] / n); tot += h[i] / n; }
+        for (int i = 0; i < 6; ++i) { fprintf(stderr, " %s=%.0f", nm[i], h[i] / n); tot += h[i] / n; }
         fprintf(stderr, " total=%.0f\n", tot);
     }
 #endif

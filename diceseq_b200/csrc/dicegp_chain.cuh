@@ -1,14 +1,20 @@
-// dicegp_chain.cuh -- the per-chain MH loop (one thread block per chain), kernel v1.
+// dicegp_chain.cuh -- the per-chain MH loop (one thread block per chain), kernel v2.
 //
-// Warp-specialised: the first S = ceil(C*Tc/32) warps are STATE warps, one thread per
-// latent value y[c,t]; they own the serial part of a step (proposal, softmax / length
-// reweighting, GP prior, MH decision, trace row).  The remaining warps are LIKELIHOOD
-// warps; each owns fixed read slices of fixed time points, keeps that time point's
-// isoform weights f in registers and accumulates prod(x_n) as (mantissa, exponent).
-// Per step the two groups meet at three block barriers (B1: f is ready, B2: partial
-// likelihoods are ready, B3: decision is known); the rest of the serial part overlaps
-// with the likelihood pass, and the device-generated random stream for step m+2 is
-// produced by the likelihood warps while the state warps write the trace row of step m.
+// 1. Exact speculative rounds.  A Metropolis-Hastings step either keeps Y_now or moves to
+//    Y_try, so the states the chain can be in after D steps form a binary tree with
+//    J = 2^D - 1 proposal nodes, all of which are known BEFORE the first decision because
+//    the proposal increments and uniforms come from a stream that does not depend on the
+//    chain (model_GP.py:329,351).  One round evaluates the posterior of all J candidate
+//    states in ONE pass over the read matrix W (J dot products per read instead of 1),
+//    then walks the tree with the ordinary accept tests.  D steps are committed per round;
+//    the arithmetic of every committed step is identical to running the steps one by one.
+//    W traffic per step drops to 1/D and so does the serial latency per step.
+// 2. Warp specialisation.  STATE warps hold one thread per (node, isoform, time) latent
+//    value and own the serial part (proposal, softmax / length reweighting, GP prior,
+//    decisions, trace rows).  LIKELIHOOD warps own fixed read slices, accumulate prod(x_n)
+//    as (mantissa, exponent) per node, and refill the random stream ring while the state
+//    warps decide.  Three block barriers per round: B1 (f ready), B2 (partial likelihoods
+//    ready), B3 (decisions known).
 #pragma once
 #include "dicegp_kernels.cuh"
 
@@ -20,132 +26,98 @@
 
 namespace dg {
 
-// named barrier 2: state warps only (barrier 0 = __syncthreads)
-__device__ __forceinline__ void bar_state(int nstate) {
-    asm volatile("bar.sync 2, %0;" ::"r"(nstate) : "memory");
+__device__ __forceinline__ void bar_state(int n) { asm volatile("bar.sync 2, %0;" ::"r"(n) : "memory"); }
+__device__ __forceinline__ void bar_lik(int n) { asm volatile("bar.sync 3, %0;" ::"r"(n) : "memory"); }
+
+// mantissa in [1,2) of a positive normal double whose high word is `hi`
+__device__ __forceinline__ double dg_mant(double x, int hi) {
+    return __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
 }
 
-// One likelihood segment: pairs p = p0, p0+stride, ... of one time point.
-//   x_n = sum_k W[n,k] f[k]                                    model_GP.py:338
+// One likelihood segment: pairs p = p0, p0+stride, ... of one time point, J candidates.
+//   x_n^(j) = sum_k W[n,k] f^(j)[k]                            model_GP.py:338
 // W block: isoform-major, row k = npairs double2 (two reads per 16-byte load; consecutive
-// lanes take consecutive pairs: conflict-free LDS.128 / coalesced LDG.128).
-// prod(x) is carried as two mantissa products (one per read of the pair) and one
-// exponent sum; anything that is not a positive normal double raises `bad`.
-template <int KC, bool LOGPATH>
+// lanes take consecutive pairs: conflict-free LDS.128 / coalesced LDG.128).  f of the J
+// candidates sits in shared memory as ff[k][JP] and is read as broadcast LDS.128.
+// prod_n x_n is carried per candidate as a mantissa product and an exponent sum; anything
+// that is not a positive normal double raises `bad` (the round is then redone with logs).
+template <int KC, int J, bool LOGPATH>
 __device__ __forceinline__ void lik_segment(const double2 *__restrict__ Wt, int npairs, int n, int C,
-                                            const double *fcol, int Tc, int p0, int stride, double &m0,
-                                            double &m1, int &e, unsigned &bad, double &logsum) {
-    constexpr int KR = KC > 0 ? KC : 1;
-    double f[KR];
-    if (KC > 0) {
-#pragma unroll
-        for (int k = 0; k < KR; ++k) f[k] = fcol[k * Tc];
-    }
+                                            const double *ffcol, int p0, int stride, double (&mm)[J],
+                                            int (&ee)[J], unsigned &bad, double (&ls)[J]) {
+    constexpr int JP = J + 1;
     int it = 0;
-#pragma unroll 2
     for (int p = p0; p < npairs; p += stride) {
-        double x0 = 0.0, x1 = 0.0;
-        if (KC > 0) {
+        double x0[J], x1[J];
 #pragma unroll
-            for (int k = 0; k < KR; ++k) {
-                const double2 w = Wt[(size_t)k * npairs + p];
-                x0 = fma(w.x, f[k], x0);
-                x1 = fma(w.y, f[k], x1);
-            }
-        } else {
-            for (int k = 0; k < C; ++k) {
-                const double2 w = Wt[(size_t)k * npairs + p];
-                const double fk = fcol[k * Tc];
-                x0 = fma(w.x, fk, x0);
-                x1 = fma(w.y, fk, x1);
+        for (int j = 0; j < J; ++j) { x0[j] = 0.0; x1[j] = 0.0; }
+        const int kmax = KC > 0 ? KC : C;
+#pragma unroll
+        for (int k = 0; k < kmax; ++k) {
+            const double2 w = Wt[(size_t)k * npairs + p];
+            const double2 *f2 = reinterpret_cast<const double2 *>(ffcol + k * JP);
+            double fj[JP];
+#pragma unroll
+            for (int q = 0; q < JP / 2; ++q) { const double2 t = f2[q]; fj[2 * q] = t.x; fj[2 * q + 1] = t.y; }
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                x0[j] = fma(w.x, fj[j], x0[j]);
+                x1[j] = fma(w.y, fj[j], x1[j]);
             }
         }
         const bool v1 = (2 * p + 1) < n;              // the pad slot of an odd block
         if (LOGPATH) {
-            logsum += log(x0);
-            if (v1) logsum += log(x1);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                ls[j] += log(x0[j]);
+                if (v1) ls[j] += log(x1[j]);
+            }
         } else {
-            const double y1 = v1 ? x1 : 1.0;
-            const int h0 = __double2hiint(x0), h1 = __double2hiint(y1);
-            bad |= (((unsigned)(h0 - 0x00100000) >= 0x7fe00000u) || ((unsigned)(h1 - 0x00100000) >= 0x7fe00000u)) ? 1u : 0u;
-            e += (h0 >> 20) + (h1 >> 20) - 2046;
-            m0 *= __hiloint2double((h0 & 0x000fffff) | 0x3ff00000, __double2loint(x0));
-            m1 *= __hiloint2double((h1 & 0x000fffff) | 0x3ff00000, __double2loint(y1));
-            if (((++it) & 511) == 0) {                 // keep the running products in range
-                const int g0 = __double2hiint(m0), g1 = __double2hiint(m1);
-                e += (g0 >> 20) + (g1 >> 20) - 2046;
-                m0 = __hiloint2double((g0 & 0x000fffff) | 0x3ff00000, __double2loint(m0));
-                m1 = __hiloint2double((g1 & 0x000fffff) | 0x3ff00000, __double2loint(m1));
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const double y1 = v1 ? x1[j] : 1.0;
+                const int h0 = __double2hiint(x0[j]), h1 = __double2hiint(y1);
+                bad |= (((unsigned)(h0 - 0x00100000) >= 0x7fe00000u) || ((unsigned)(h1 - 0x00100000) >= 0x7fe00000u)) ? 1u : 0u;
+                ee[j] += (h0 >> 20) + (h1 >> 20) - 2046;
+                mm[j] *= dg_mant(x0[j], h0) * dg_mant(y1, h1);
+            }
+            if (((++it) & 255) == 0) {                 // keep the running products in range
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int g = __double2hiint(mm[j]);
+                    ee[j] += (g >> 20) - 1023;
+                    mm[j] = dg_mant(mm[j], g);
+                }
             }
         }
     }
 }
 
-// shapes and shared arrays of the chain a block is working on
-struct ChainCtx {
-    int C, Tc, CT, CTm;               // CTm = (C-1)*Tc free latent values
-    int tid, nthreads, lane, warp, nwarps;
-    int nstate, S, NWL;               // state threads (multiple of 32), state warps, likelihood warps
-    double *ytry, *fsi, *ex, *gs, *pr, *qq, *zb;
-    double *kinv, *pfac, *ijs, *jcon, *sqs;
-    double *red, *bc, *gw;
-    int *redi, *rel, *ncnt, *seg;
-    unsigned *redb;
-    const double *Wc;                 // shared or global
-    double prior_const;
-};
-
-// Likelihood pass of one likelihood warp over its segments; leaves (mantissa, exponent,
-// bad) of the warp in red/redi/redb[wl].
-template <int KC>
-__device__ __forceinline__ void lik_warp_pass(const ChainCtx &s, int wl, int nseg) {
-    double m0 = 1.0, m1 = 1.0, dummy = 0.0;
-    int e = 0;
-    unsigned bad = 0u;
-    for (int sg = wl; sg < nseg; sg += s.NWL) {
-        const int tt = s.seg[3 * sg], first = s.seg[3 * sg + 1], stride = s.seg[3 * sg + 2];
-        const int r0 = s.rel[tt], npairs = (s.rel[tt + 1] - r0) >> 1;
-        const double2 *Wt = reinterpret_cast<const double2 *>(s.Wc + (size_t)s.C * r0);
-        lik_segment<KC, false>(Wt, npairs, s.ncnt[tt], s.C, s.fsi + tt, s.Tc, first + s.lane, stride, m0, m1, e, bad, dummy);
-        // a warp that walks many segments keeps its products in range
-        const int g0 = __double2hiint(m0), g1 = __double2hiint(m1);
-        e += (g0 >> 20) + (g1 >> 20) - 2046;
-        m0 = __hiloint2double((g0 & 0x000fffff) | 0x3ff00000, __double2loint(m0));
-        m1 = __hiloint2double((g1 & 0x000fffff) | 0x3ff00000, __double2loint(m1));
-    }
-    double m = m0 * m1;                                     // < 4
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        m *= __shfl_xor_sync(0xffffffffu, m, off);          // < 4^32 = 2^64
-        e += __shfl_xor_sync(0xffffffffu, e, off);
-        bad |= __shfl_xor_sync(0xffffffffu, bad, off);
-    }
-    if (s.lane == 0) {
-        const int g = __double2hiint(m);
-        s.red[wl] = __hiloint2double((g & 0x000fffff) | 0x3ff00000, __double2loint(m));
-        s.redi[wl] = e + (g >> 20) - 1023;
-        s.redb[wl] = bad;
-    }
-}
-
-// Slow path (some x_n is 0 / negative / non-finite): the same sum with real logarithms so
+// Slow path (some x_n is 0 / negative / non-finite): the same sums with real logarithms so
 // that -inf and NaN propagate like np.log(...).sum() does (model_GP.py:344).
-template <int KC>
+template <int KC, int J>
 __device__ __noinline__ void lik_warp_pass_log(const double *Wc, const int *seg, const int *rel, const int *ncnt,
-                                               const double *fsi, double *red, int C, int Tc, int NWL, int lane,
-                                               int wl, int nseg) {
-    double m0 = 1.0, m1 = 1.0, ls = 0.0;
-    int e = 0;
+                                               const double *ff, double *red, int C, int NWL, int lane, int wl,
+                                               int nseg) {
+    constexpr int JP = J + 1;
+    double mm[J], ls[J];
+    int ee[J];
     unsigned bad = 0u;
+#pragma unroll
+    for (int j = 0; j < J; ++j) { mm[j] = 1.0; ls[j] = 0.0; ee[j] = 0; }
     for (int sg = wl; sg < nseg; sg += NWL) {
         const int tt = seg[3 * sg], first = seg[3 * sg + 1], stride = seg[3 * sg + 2];
         const int r0 = rel[tt], npairs = (rel[tt + 1] - r0) >> 1;
         const double2 *Wt = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0);
-        lik_segment<KC, true>(Wt, npairs, ncnt[tt], C, fsi + tt, Tc, first + lane, stride, m0, m1, e, bad, ls);
+        lik_segment<KC, J, true>(Wt, npairs, ncnt[tt], C, ff + (size_t)tt * C * JP, first + lane, stride, mm, ee, bad, ls);
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, off);
-    if (lane == 0) red[wl] = ls;
+    for (int j = 0; j < J; ++j) {
+        double v = ls[j];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[j * DG_MAXWARPS + wl] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -236,50 +208,118 @@ __device__ __noinline__ int build_segments(int *seg, const int *rel, int Tc, int
     return k;
 }
 
+// Out-of-line copies of the long math routines used on the round loop: the loop body has
+// to stay small enough for the instruction cache (the serial part runs in one warp, which
+// cannot hide instruction-fetch latency).
+__device__ __noinline__ double dg_log(double x) { return log(x); }
+
+// Fill stream ring entries for steps [s0, s1): increments delta[c,t] and log(u).
+// Device stream: Philox normals z (Box-Muller, both outputs of a pair used), then
+// delta = sqrt(jump_scale[c]) * (z[c,:] @ A_K).  Host stream: delta and u come from the
+// uploaded chunk.  Called by `nprod` threads (index `pt`) which must ALL call it: they
+// synchronise on __syncthreads (all_threads) or on the likelihood-warp barrier.
+__device__ __noinline__ void produce_stream(bool dev_stream, int s0, int s1, int pt, int nprod, bool all_threads,
+                                            double *zring, double *dring, int RING, int CT, int CTm, int Tc,
+                                            const double *pfac, const double *sqs, uint64_t seed, int64_t sid,
+                                            const double *dblk, const double *ublk, int m_start) {
+    if (dev_stream) {
+        const int npair = (CTm + 1) >> 1;
+        for (int s = s0; s < s1; ++s) {
+            double *z = zring + (s % RING) * CT;
+            for (int i = pt; i < npair; i += nprod) {
+                double z0, z1;
+                dg_normal_pair(seed, sid, (uint32_t)s, (uint32_t)i, z0, z1);
+                z[2 * i] = z0;
+                if (2 * i + 1 < CTm) z[2 * i + 1] = z1;
+            }
+            if (pt == nprod - 1) dring[(s % RING) * CT + CT - 1] = dg_log(dg_uniform(seed, sid, (uint32_t)s));
+        }
+        if (all_threads) __syncthreads(); else bar_lik(nprod);
+        for (int s = s0; s < s1; ++s) {
+            const double *z = zring + (s % RING) * CT;
+            double *d = dring + (s % RING) * CT;
+            for (int i = pt; i < CTm; i += nprod) {
+                const int c = i / Tc, t = i - c * Tc;
+                double a = 0.0;
+                for (int j = 0; j < Tc; ++j) a = fma(z[c * Tc + j], pfac[j * Tc + t], a);
+                d[i] = sqs[c] * a;
+            }
+        }
+    } else {
+        for (int s = s0; s < s1; ++s) {
+            double *d = dring + (s % RING) * CT;
+            const double *src = dblk + (size_t)(s - m_start) * CTm;
+            for (int i = pt; i < CTm; i += nprod) d[i] = src[i];
+            if (pt == nprod - 1) d[CT - 1] = dg_log(ublk[s - m_start]);
+        }
+    }
+}
+
+// Trace page of row `step` (first touch allocates from the pool).  Returns -1 when the
+// pool is exhausted.  Rare: one call per 2^pshift steps.
+__device__ __noinline__ long long trace_page(int64_t *ptab, int step, int pshift, int rowlen,
+                                             unsigned long long *pool_head, int64_t pool_cap) {
+    long long pg = __ldcg(ptab + (step >> pshift));
+    if (pg < 0) {
+        const unsigned long long need = (unsigned long long)rowlen << pshift;
+        const unsigned long long off = atomicAdd(pool_head, need);
+        if (off + need <= (unsigned long long)pool_cap) {
+            pg = (long long)off;
+            ptab[step >> pshift] = pg;
+        }
+    }
+    return pg;
+}
+
 // ---------------------------------------------------------------------------------------
 // one chain, up to n_steps steps.  `slot` indexes the host stream blocks.
 // ---------------------------------------------------------------------------------------
-template <int KC, bool W_IN_SMEM>
+template <int KC, bool W_IN_SMEM, int D>
 __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArgs &sa, int chain,
                           int slot, int n_steps, double *smem, int use_tma) {
-    ChainCtx s;
-    s.tid = threadIdx.x; s.nthreads = blockDim.x;
-    s.lane = s.tid & 31; s.warp = s.tid >> 5; s.nwarps = s.nthreads >> 5;
+    constexpr int J = (1 << D) - 1;
+    constexpr int JP = J + 1;
+    constexpr int RING = 2 * D;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     if (ct.state[chain] != 0) return;                    // already finished (block-uniform)
 
     const int g = ct.gene[chain], t0 = ct.t0[chain];
-    const int C = gt.C[g], Tc = ct.Tc[chain], T = gt.T;
-    s.C = C; s.Tc = Tc; s.CT = C * Tc; s.CTm = (C - 1) * Tc;
-    s.S = (s.CT + 31) >> 5; s.nstate = s.S << 5; s.NWL = s.nwarps - s.S;
-    const SmLayout L = dg_layout(C, Tc, s.nwarps);
-    s.ytry = smem + L.ytry; s.fsi = smem + L.fsi; s.ex = smem + L.ex; s.gs = smem + L.gs;
-    s.pr = smem + L.pr; s.qq = smem + L.qq; s.zb = smem + L.zb; s.kinv = smem + L.kinv;
-    s.pfac = smem + L.pfac; s.ijs = smem + L.ijs; s.jcon = smem + L.jcon;
-    s.sqs = smem + L.sqs; s.red = smem + L.red; s.redi = reinterpret_cast<int *>(smem + L.redi);
-    s.redb = reinterpret_cast<unsigned *>(smem + L.redb); s.bc = smem + L.bc; s.gw = smem + L.gw;
-    s.rel = reinterpret_cast<int *>(smem + L.rel); s.ncnt = s.rel + (Tc + 1);
-    s.seg = reinterpret_cast<int *>(smem + L.seg);
+    const int C = KC > 0 ? KC : gt.C[g];
+    const int Tc = ct.Tc[chain], T = gt.T;
+    const int CT = C * Tc, CTm = (C - 1) * Tc;
+    const int S = (J * CT + 31) >> 5, nstate = S << 5, NWL = nwarps - S;
+    const SmLayout L = dg_layout(C, Tc, nwarps, D);
+    double *ycand = smem + L.ycand, *psic = smem + L.psic, *gs = smem + L.gs, *ex = smem + L.ex;
+    double *pr = smem + L.pr, *qq = smem + L.qq, *ff = smem + L.ff, *zring = smem + L.zring, *dring = smem + L.dring;
+    double *kinv = smem + L.kinv, *pfac = smem + L.pfac, *ijs = smem + L.ijs, *jcon = smem + L.jcon, *sqs = smem + L.sqs;
+    double *red = smem + L.red, *bc = smem + L.bc, *gw = smem + L.gw;
+    int *redi = reinterpret_cast<int *>(smem + L.redi);
+    unsigned *redb = reinterpret_cast<unsigned *>(smem + L.redb);
+    int *rel = reinterpret_cast<int *>(smem + L.rel), *ncnt = rel + (Tc + 1);
+    int *seg = reinterpret_cast<int *>(smem + L.seg);
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + L.mbar);
     double *Wsm = smem + L.w;
-    s.prior_const = ct.prior_const[chain];
-    const bool is_state = s.tid < s.nstate;
-    const int wl = s.warp - s.S;                          // likelihood-warp index (>= 0 for those)
+    const double prior_const = ct.prior_const[chain];
+    const bool is_state = tid < nstate;
+    const int wl = warp - S;                              // likelihood-warp index (>= 0 for those)
 
     const int32_t *roff = gt.roff + (size_t)g * (T + 1) + t0;
     const int r_first = roff[0];
     const int r_total = roff[Tc] - r_first;
     const double *Wg = gt.W + gt.woff[g] + (size_t)C * r_first;
     const size_t wbytes = (size_t)C * r_total * sizeof(double);
+    const double *Wc = W_IN_SMEM ? Wsm : Wg;
 
     // ---- stage W (TMA bulk copy, asynchronous) and the small per-chain constants --------
     if (W_IN_SMEM) {
         if (use_tma) {
-            if (s.tid == 0) {
+            if (tid == 0) {
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dg_smem_u32(mbar)));
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
             __syncthreads();
-            if (s.tid == 0 && wbytes > 0) {
+            if (tid == 0 && wbytes > 0) {
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
                                  dg_smem_u32(mbar)), "r"((uint32_t)wbytes) : "memory");
                 const uint32_t kChunk = 32768u;
@@ -298,33 +338,30 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             const double2 *src = reinterpret_cast<const double2 *>(Wg);
             double2 *dst = reinterpret_cast<double2 *>(Wsm);
             const size_t n2 = wbytes / sizeof(double2);
-            for (size_t i = s.tid; i < n2; i += s.nthreads) dst[i] = src[i];
+            for (size_t i = tid; i < n2; i += nthreads) dst[i] = src[i];
         }
-        s.Wc = Wsm;
-    } else {
-        s.Wc = Wg;
     }
-    for (int i = s.tid; i <= Tc; i += s.nthreads) s.rel[i] = roff[i] - r_first;
-    for (int i = s.tid; i < Tc; i += s.nthreads) s.ncnt[i] = gt.ncnt[(size_t)g * T + t0 + i];
+    for (int i = tid; i <= Tc; i += nthreads) rel[i] = roff[i] - r_first;
+    for (int i = tid; i < Tc; i += nthreads) ncnt[i] = gt.ncnt[(size_t)g * T + t0 + i];
     {
         const double *pool = ct.pool;
-        const double *kinv = pool + ct.kinv_off[chain];
-        for (int i = s.tid; i < Tc * Tc; i += s.nthreads) s.kinv[i] = kinv[i];
+        const double *kv = pool + ct.kinv_off[chain];
+        for (int i = tid; i < Tc * Tc; i += nthreads) kinv[i] = kv[i];
         if (ct.pf_off[chain] >= 0) {
             const double *pf = pool + ct.pf_off[chain];
-            for (int i = s.tid; i < Tc * Tc; i += s.nthreads) s.pfac[i] = pf[i];
+            for (int i = tid; i < Tc * Tc; i += nthreads) pfac[i] = pf[i];
         }
         const double *js = pool + ct.js_off[chain], *jc = pool + ct.jc_off[chain];
-        for (int i = s.tid; i < C - 1; i += s.nthreads) {
-            s.ijs[i] = 1.0 / js[i];
-            s.sqs[i] = sqrt(js[i]);
-            s.jcon[i] = jc[i];
+        for (int i = tid; i < C - 1; i += nthreads) {
+            ijs[i] = 1.0 / js[i];
+            sqs[i] = sqrt(js[i]);
+            jcon[i] = jc[i];
         }
     }
     const int M = ct.M[chain], initial = ct.initial[chain], gap = ct.gap[chain];
     int m = ct.m_next[chain];
     double *st = ct.st + ct.st_off[chain];
-    const int rowlen = 2 * s.CT + 2;
+    const int rowlen = 2 * CT + 2;
     int64_t *ptab = ct.ptab + ct.ptab_off[chain];
     const int pshift = ct.pshift[chain];
     const int pmask = (1 << pshift) - 1;
@@ -333,22 +370,25 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     const int64_t sid = ct.stream_id ? ct.stream_id[chain] : (int64_t)chain;
     const bool dev_stream = sa.mode != 0;
 
-    // per state thread: its latent value (c, t); current state lives in registers
-    const int si = s.tid;                                 // state index = c*Tc + t
-    const bool s_act = is_state && si < s.CT;             // owns a value
-    const bool s_free = is_state && si < s.CTm;           // value is sampled (c < C-1)
-    const int sc = s_act ? si / Tc : 0;
-    const int stt = s_act ? si - sc * Tc : 0;
-    double y_now = 0.0, psi_now = 0.0;
+    // ---- state lanes: lane s = node*CT + (c*Tc + t) ----------------------------------------
+    const bool s_act = is_state && tid < J * CT;          // owns a latent value of a candidate node
+    const int nd_j = s_act ? tid / CT : 0;                // candidate node (heap order)
+    const int si = s_act ? tid - nd_j * CT : 0;           // c*Tc + t
+    const int sc = si / Tc, stt = si - sc * Tc;
+    const bool s_free = s_act && sc < C - 1;              // value is sampled (c < C-1)
+    int nd_depth = 0;                                     // depth of the node = step offset it proposes
+    while ((2 << nd_depth) <= nd_j + 1) ++nd_depth;
+    const int nd_path = (nd_j + 1) - (1 << nd_depth);     // edge bits root->node, MSB first: 1 = accepted parent
+    double y_now = 0.0, psi_now = 0.0;                    // replicated over the J node groups
     double P_now = 0.0, L_now = 0.0;                      // thread 0
     int cnt = 0, flags = 0;
-    if (s.tid == 0) { cnt = ct.cnt[chain]; flags = ct.flags[chain]; }
+    if (tid == 0) { cnt = ct.cnt[chain]; flags = ct.flags[chain]; }
     const double len_own = s_act ? gt.len[gt.lenoff[g] + (size_t)(t0 + stt) * C + sc] : 0.0;
 
     __syncthreads();                                      // rel / ncnt visible
-    if (s.tid == 0) s.bc[6] = (double)build_segments(s.seg, s.rel, Tc, s.NWL);
-    if (m > 0 && s_act) { y_now = st[si]; psi_now = st[s.CT + si]; }
-    if (m > 0 && s.tid == 0) { P_now = st[2 * s.CT]; L_now = st[2 * s.CT + 1]; }
+    if (tid == 0) bc[15] = (double)build_segments(seg, rel, Tc, NWL);
+    if (m > 0 && s_act) { y_now = st[si]; psi_now = st[CT + si]; }
+    if (m > 0 && tid == 0) { P_now = st[2 * CT]; L_now = st[2 * CT + 1]; }
     if (W_IN_SMEM && use_tma && wbytes > 0) {
         uint32_t ok = 0;                                  // wait for the bulk copy (phase 0)
         while (!ok) {
@@ -360,238 +400,281 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         }
     }
     __syncthreads();
-    const int nseg = (int)s.bc[6];
+    const int nseg = (int)bc[15];
 
     const int m_start = m;
     const int m_end = (m_start + n_steps < M) ? (m_start + n_steps) : M;
     int state = 0, m_ret = 0;
-    double *page = nullptr;                               // state threads: page of the row being written
-
-    // ---- stream set-up ---------------------------------------------------------------------
-    const double *dblk = nullptr, *ublk = nullptr;
-    double d_next = 0.0, lu_next = 0.0;
-    if (!dev_stream) {
-        dblk = sa.delta + sa.delta_off[slot];
-        ublk = sa.u + sa.u_off[slot];
-        if (m < m_end) {
-            if (s_free) d_next = dblk[si];
-            if (s.tid == 0) lu_next = log(ublk[0]);
-        }
-    } else {
-        // z and log(u) of the first two steps (later ones are produced two steps ahead by
-        // the likelihood warps); slot CT-1 of a z buffer holds log(u)
-        for (int k = 0; k < 2; ++k) {
-            const int mm = m + k;
-            for (int i = s.tid; i < s.CTm; i += s.nthreads)
-                s.zb[(mm & 1) * s.CT + i] = dg_normal(sa.seed, sid, (uint32_t)mm, (uint32_t)i);
-            if (s.tid == s.nthreads - 1) s.zb[(mm & 1) * s.CT + s.CT - 1] = log(dg_uniform(sa.seed, sid, (uint32_t)mm));
-        }
-        __syncthreads();
-    }
+    long long page_cur = -1;                              // thread 0: page of the last row written
+    const double *dblk = dev_stream ? nullptr : sa.delta + sa.delta_off[slot];
+    const double *ublk = dev_stream ? nullptr : sa.u + sa.u_off[slot];
+    // stream ring: entries for steps [m, m + RING) (clipped to the chunk)
+    produce_stream(dev_stream, m, min(m + RING, m_end), tid, nthreads, true, zring, dring, RING, CT, CTm, Tc, pfac, sqs,
+                   sa.seed, sid, dblk, ublk, m_start);
+    __syncthreads();
 #ifdef DG_PROFILE
     long long dg_prof[10];
     long long dg_t0 = clock64();
     for (int i = 0; i < 10; ++i) dg_prof[i] = 0;
 #endif
 
-    // it == -1: evaluate the start value (model_GP.py:275-292) with the same machinery as a
-    // step (always "accepted", no trace row), then steps m .. m_end-1
-    for (int it = (m == 0 ? -1 : m); it < m_end; ++it) {
-        const bool init = it < 0;
-        const int mcur = init ? 0 : it;
-        double y_try = 0.0, e_try = 1.0, g_own = 0.0, psi_try = 0.0, lu_cur = 0.0;
-        // ================= S phase (state warps): proposal -> f =================
+    bool init = (m == 0);                                 // evaluate the start value first (model_GP.py:275-292)
+    while (m < m_end || init) {
+        // steps this round may commit: up to D, not past the chunk, not past a check step
+        int nd_max = 0;
+        if (!init) {
+            int mc = m > initial ? m : initial;
+            mc += (gap - mc % gap) % gap;                 // next step with m >= initial and m % gap == 0
+            nd_max = min(D, min(m_end - m, mc - m + 1));
+        }
+        // ================= S phase (state warps): candidates -> f =================
+        double y_c = 0.0, base_c = 0.0, e_c = 1.0, g_c = 0.0, psi_c = 0.0;
         if (is_state) {
-            if (init) {
-                const double *y0 = ct.y0_off[chain] >= 0 ? ct.pool + ct.y0_off[chain] : nullptr;
-                if (s_act) y_try = y0 ? y0[si] : 0.0;                       // Y_now = Ymean (:275)
-            } else if (s_free) {
-                double d;
-                if (!dev_stream) {
-                    d = d_next;
-                } else {
-                    const double *z = s.zb + (mcur & 1) * s.CT + sc * Tc;
-                    double a = 0.0;
-                    for (int j = 0; j < Tc; ++j) a = fma(z[j], s.pfac[j * Tc + stt], a);
-                    d = s.sqs[sc] * a;
-                }
-                y_try = d + y_now;                                           // (:329) numpy adds the mean last
-            }                                                                // else Y_try[C-1,:] stays 0 (:295)
-            if (s.tid == 0 && !init) lu_cur = dev_stream ? s.zb[(mcur & 1) * s.CT + s.CT - 1] : lu_next;
             if (s_act) {
-                e_try = exp(y_try);
-                g_own = len_own * e_try;
-                s.ytry[si] = y_try;
-                s.ex[si] = e_try;
-                s.gs[si] = g_own;
+                if (init) {
+                    const double *y0 = ct.y0_off[chain] >= 0 ? ct.pool + ct.y0_off[chain] : nullptr;
+                    y_c = y0 ? y0[si] : 0.0;                                 // Y_now = Ymean (:275)
+                    base_c = y_c;
+                } else if (s_free) {
+                    // state before this node proposes: Y_now moved through its accepted ancestors
+                    double cur = y_now;
+#pragma unroll
+                    for (int i = 0; i < D - 1; ++i) {
+                        if (i < nd_depth && i < nd_max && ((nd_path >> (nd_depth - 1 - i)) & 1))
+                            cur = dring[((m + i) % RING) * CT + si] + cur;
+                    }
+                    const double dl = (nd_depth < nd_max) ? dring[((m + nd_depth) % RING) * CT + si] : 0.0;
+                    y_c = dl + cur;                                          // (:329) numpy adds the mean last
+                    base_c = cur;
+                }                                                            // else Y_try[C-1,:] stays 0 (:295)
+                e_c = exp(y_c);
+                g_c = len_own * e_c;
+                ycand[tid] = y_c;
+                ex[tid] = e_c;
+                gs[tid] = g_c;
             }
-            bar_state(s.nstate);
+            bar_state(nstate);
             if (s_act) {
                 // fsi = len*psi / sum(len*psi) with psi = e/sum(e): the common 1/sum(e) cancels
                 // (model_GP.py:335-337; one division on the critical path instead of two)
-                const double sg = dg_np_sum(s.gs + stt, C, Tc);
-                s.fsi[si] = g_own / sg;
+                const double sg = dg_np_sum(gs + nd_j * CT + stt, C, Tc);
+                ff[(stt * C + sc) * JP + nd_j] = g_c / sg;
             }
         }
         __syncthreads();                                                     // B1: f ready
         DG_TICK(0);
         // ================= likelihood warps || rest of the serial part =================
         if (!is_state) {
-            lik_warp_pass<KC>(s, wl, nseg);
-        } else {
-            if (!dev_stream && !init && mcur + 1 < m_end) {                  // host stream: prefetch
-                if (s_free) d_next = dblk[(size_t)(mcur + 1 - m_start) * s.CTm + si];
-                if (s.tid == 0) lu_next = log(ublk[mcur + 1 - m_start]);
+            double mm[J], lsd[J];
+            int ee[J];
+            unsigned bad = 0u;
+#pragma unroll
+            for (int j = 0; j < J; ++j) { mm[j] = 1.0; ee[j] = 0; lsd[j] = 0.0; }
+            for (int sg = wl; sg < nseg; sg += NWL) {
+                const int tt = seg[3 * sg], first = seg[3 * sg + 1], stride = seg[3 * sg + 2];
+                const int r0 = rel[tt], npairs = (rel[tt + 1] - r0) >> 1;
+                const double2 *Wt = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0);
+                lik_segment<KC, J, false>(Wt, npairs, ncnt[tt], C, ff + (size_t)tt * C * JP, first + lane, stride, mm, ee, bad, lsd);
+#pragma unroll
+                for (int j = 0; j < J; ++j) {                                // a warp walking many segments stays in range
+                    const int gg = __double2hiint(mm[j]);
+                    ee[j] += (gg >> 20) - 1023;
+                    mm[j] = dg_mant(mm[j], gg);
+                }
             }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    mm[j] *= __shfl_xor_sync(0xffffffffu, mm[j], off);       // < 2^32
+                    ee[j] += __shfl_xor_sync(0xffffffffu, ee[j], off);
+                }
+                bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int gg = __double2hiint(mm[j]);
+                    red[j * DG_MAXWARPS + wl] = dg_mant(mm[j], gg);
+                    redi[j * DG_MAXWARPS + wl] = ee[j] + (gg >> 20) - 1023;
+                }
+                redb[wl] = bad;
+            }
+        } else {
             if (s_act) {
-                const double se = dg_np_sum(s.ex + stt, C, Tc);
-                psi_try = e_try / se;                                        // (:335)
+                const double se = dg_np_sum(ex + nd_j * CT + stt, C, Tc);
+                psi_c = e_c / se;                                            // (:335)
+                psic[tid] = psi_c;
             }
             // GP prior (:332) and proposal density (:330-331): x K^-1 x as (x K^-1)[t] * x[t]
             if (s_free) {
-                const double *yc = s.ytry + sc * Tc;
+                const double *yc = ycand + nd_j * CT + sc * Tc;
                 double r = 0.0;
-                for (int j = 0; j < Tc; ++j) r = fma(yc[j], s.kinv[j * Tc + stt], r);
-                s.pr[si] = r * y_try;
-                s.qq[si] = y_now - y_try;                                    // d = Y_now - Y_try
+                for (int j = 0; j < Tc; ++j) r = fma(yc[j], kinv[j * Tc + stt], r);
+                pr[tid] = r * y_c;
+                qq[tid] = base_c - y_c;                                      // d = Y_now - Y_try
             }
-            bar_state(s.nstate);
+            bar_state(nstate);
             double qpart = 0.0;
-            if (s_free && !init) {
-                const double *dc = s.qq + sc * Tc;
+            if (s_free) {
+                const double *dc = qq + nd_j * CT + sc * Tc;
                 double dq = 0.0;
-                for (int j = 0; j < Tc; ++j) dq = fma(dc[j], s.kinv[j * Tc + stt], dq);
-                qpart = dq * (y_now - y_try);
+                for (int j = 0; j < Tc; ++j) dq = fma(dc[j], kinv[j * Tc + stt], dq);
+                qpart = dq * (base_c - y_c);
             }
-            bar_state(s.nstate);                                             // everyone has read qq
-            if (s_free) s.qq[si] = qpart;
-            bar_state(s.nstate);
-            if (s.tid < C - 1) {
-                const int c = s.tid;
+            bar_state(nstate);                                               // everyone has read qq
+            if (s_free) qq[tid] = qpart;
+            bar_state(nstate);
+            if (tid < J * (C - 1)) {                                         // lane (node, c): sums over t
+                const int jn = tid / (C - 1), c = tid - jn * (C - 1);
+                const double *prc = pr + jn * CT + c * Tc, *qc = qq + jn * CT + c * Tc;
                 double a = 0.0, b = 0.0;
-                for (int t = 0; t < Tc; ++t) { a += s.pr[c * Tc + t]; b += s.qq[c * Tc + t]; }
-                s.pr[c * Tc] = s.prior_const - a / 2.0;
-                s.qq[c * Tc] = s.jcon[c] - (b * s.ijs[c]) / 2.0;
+                for (int t = 0; t < Tc; ++t) { a += prc[t]; b += qc[t]; }
+                gs[jn * CT + c] = prior_const - a / 2.0;                     // gs / ex are free after B1
+                ex[jn * CT + c] = jcon[c] - (b * ijs[c]) / 2.0;
             }
-            bar_state(s.nstate);
-            if (s.tid == 0) {
+            bar_state(nstate);
+            if (tid < J) {
                 double prior = 0.0, Q = 0.0;                                 // c ascending (:312-332)
-                for (int c = 0; c < C - 1; ++c) {
-                    prior += s.pr[c * Tc];
-                    if (!init) Q += s.qq[c * Tc];
-                }
-                s.bc[0] = prior;
-                s.bc[1] = Q;
+                for (int c = 0; c < C - 1; ++c) { prior += gs[tid * CT + c]; Q += ex[tid * CT + c]; }
+                bc[16 + tid] = prior;
+                bc[16 + J + tid] = init ? 0.0 : Q;
             }
         }
         DG_TICK(1);
         __syncthreads();                                                     // B2: partial likelihoods ready
         DG_TICK(2);
-        // ================= decision (warp 0; thread 0 decides) =================
+        // ================= decisions (warp 0; thread 0 walks the tree) =================
         bool redo = false;
         do {
-            if (s.warp == 0) {
-                double lik;
+            if (warp == 0) {
+                double lik[J];
                 unsigned bad = 0u;
                 if (!redo) {
-                    double mm = s.lane < s.NWL ? s.red[s.lane] : 1.0;
-                    int ee = s.lane < s.NWL ? s.redi[s.lane] : 0;
-                    bad = s.lane < s.NWL ? s.redb[s.lane] : 0u;
+                    double mm[J];
+                    int ee[J];
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        mm[j] = lane < NWL ? red[j * DG_MAXWARPS + lane] : 1.0;
+                        ee[j] = lane < NWL ? redi[j * DG_MAXWARPS + lane] : 0;
+                    }
+                    bad = lane < NWL ? redb[lane] : 0u;
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) {
-                        mm *= __shfl_xor_sync(0xffffffffu, mm, off);         // < 2^32
-                        ee += __shfl_xor_sync(0xffffffffu, ee, off);
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            mm[j] *= __shfl_xor_sync(0xffffffffu, mm[j], off);   // < 2^32
+                            ee[j] += __shfl_xor_sync(0xffffffffu, ee[j], off);
+                        }
                         bad |= __shfl_xor_sync(0xffffffffu, bad, off);
                     }
-                    lik = fma((double)ee, 0.693147180559945309417232121458, log(mm));
+#pragma unroll
+                    for (int j = 0; j < J; ++j) lik[j] = fma((double)ee[j], 0.693147180559945309417232121458, dg_log(mm[j]));
                 } else {
-                    lik = 0.0;
-                    for (int w = 0; w < s.NWL; ++w) lik += s.red[w];
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        double a = 0.0;
+                        for (int w = 0; w < NWL; ++w) a += red[j * DG_MAXWARPS + w];
+                        lik[j] = a;
+                    }
                 }
-                if (s.lane == 0) {
-                    s.bc[3] = bad ? 1.0 : 0.0;
+                if (lane == 0) {
+                    bc[3] = bad ? 1.0 : 0.0;
                     if (!bad) {
-                        const double Q = s.bc[1];
-                        const double P_try = s.bc[0] + lik;
-                        bool acc;
                         if (init) {
-                            acc = true;                                      // P_now / L_now of the start value
+                            L_now = lik[0];
+                            P_now = bc[16] + lik[0];                         // (:284-292)
+                            if (!isfinite(P_now)) flags |= 1;
+                            bc[4] = 0.0;                                     // steps committed
+                            bc[5] = 0.0;                                     // final node
+                            bc[6] = 0.0;
                         } else {
-                            // alpha = exp(min(a, 0)), accept iff u < alpha (:348-351): tested in the
-                            // log domain, log(u) having been taken off the critical path
-                            const double a = ((P_try + Q) - P_now) - Q;
-                            acc = (a >= 0.0) || (lu_cur < a);                // NaN a: both false
-                            if (acc) ++cnt;
-                        }
-                        if (!isfinite(P_try)) flags |= 1;
-                        if (acc) { P_now = P_try; L_now = lik; }
-                        // trace page of row m (allocated on first touch; the first page always exists)
-                        long long pg = 0;
-                        if (!init && (page == nullptr || (mcur & pmask) == 0)) {
-                            pg = __ldcg(ptab + (mcur >> pshift));
-                            if (pg < 0) {
-                                const unsigned long long need = (unsigned long long)rowlen << pshift;
-                                const unsigned long long off = atomicAdd(ct.pool_head, need);
-                                if (off + need <= (unsigned long long)ct.pool_cap) {
-                                    pg = (long long)off;
-                                    ptab[mcur >> pshift] = pg;
-                                }
+                            // trace pages of the rows this round may write (first touch allocates)
+                            int nd_ok = nd_max;
+                            for (int d = 0; d < nd_max; ++d) {
+                                const int step = m + d;
+                                if (page_cur < 0 || (step & pmask) == 0)
+                                    page_cur = trace_page(ptab, step, pshift, rowlen, ct.pool_head, ct.pool_cap);
+                                if (page_cur < 0) { nd_ok = d; break; }
+                                bc[32 + d] = __longlong_as_double(page_cur);
                             }
+                            // walk the tree: alpha = exp(min(a, 0)), accept iff u < alpha (:348-351),
+                            // tested in the log domain with log(u) taken off the critical path
+                            int node = 0, cur = -1;
+                            for (int d = 0; d < nd_ok; ++d) {
+                                double likn = lik[0], priorn = bc[16 + node], Q = bc[16 + J + node];
+#pragma unroll
+                                for (int j = 1; j < J; ++j) if (j == node) likn = lik[j];
+                                const double P_try = priorn + likn;
+                                const double a = ((P_try + Q) - P_now) - Q;
+                                const double lu = dring[((m + d) % RING) * CT + CT - 1];
+                                const bool acc = (a >= 0.0) || (lu < a);     // NaN a: both false
+                                if (!isfinite(P_try)) flags |= 1;
+                                if (acc) { ++cnt; P_now = P_try; L_now = likn; cur = node; }
+                                bc[40 + d] = (double)cur;                    // state after step m+d
+                                bc[48 + d] = P_now;                          // Pro_all[m+d]  (:362)
+                                bc[56 + d] = L_now;                          // Lik_all[m+d]  (:363)
+                                node = 2 * node + (acc ? 2 : 1);
+                            }
+                            bc[4] = (double)nd_ok;
+                            bc[5] = (double)cur;
+                            bc[6] = (nd_ok < nd_max) ? 1.0 : 0.0;            // trace pool exhausted
                         }
-                        s.bc[4] = acc ? 1.0 : 0.0;
-                        s.bc[5] = __longlong_as_double(pg);
                     }
                 }
             }
-            __syncthreads();                                                 // B3: decision (or redo request)
-            redo = s.bc[3] != 0.0;
+            __syncthreads();                                                 // B3: decisions (or redo request)
+            redo = bc[3] != 0.0;
             if (redo) {                                                      // rare: some x_n was not a positive normal
-                if (!is_state) lik_warp_pass_log<KC>(s.Wc, s.seg, s.rel, s.ncnt, s.fsi, s.red, C, Tc, s.NWL, s.lane, wl, nseg);
+                if (!is_state) lik_warp_pass_log<KC, J>(Wc, seg, rel, ncnt, ff, red, C, NWL, lane, wl, nseg);
                 __syncthreads();
             }
         } while (redo);
         DG_TICK(3);
-        // ================= update + trace row (state warps) || stream production (others) ======
-        const long long pg_new = __double_as_longlong(s.bc[5]);
+        // ================= update + trace rows (state warps) || stream refill (others) ======
+        const int nd = (int)bc[4];
+        const int fin = (int)bc[5];
+        const bool nomem = bc[6] != 0.0;
         if (is_state) {
-            if (s.bc[4] != 0.0 && s_act) { y_now = y_try; psi_now = psi_try; }
-            if (!init) {
-                if (page == nullptr || (mcur & pmask) == 0) page = pg_new >= 0 ? ct.trace + pg_new : nullptr;
-                if (page != nullptr) {
-                    double *row = page + (size_t)(mcur & pmask) * rowlen;
-                    if (s_act) {
-                        row[si] = psi_now;                                   // Psi_all[m]  (:365)
-                        row[s.CT + si] = y_now;                              // Y_all[m]    (:364)
-                    }
-                    if (s.tid == 0) {
-                        row[2 * s.CT] = P_now;                               // Pro_all[m]  (:362)
-                        row[2 * s.CT + 1] = L_now;                           // Lik_all[m]  (:363)
-                    }
+            if (s_act && nd_j == 0) {                                        // primary lanes write the rows
+                for (int d = 0; d < nd; ++d) {
+                    const int node = (int)bc[40 + d];
+                    const int step = m + d;
+                    double *row = ct.trace + __double_as_longlong(bc[32 + d]) + (size_t)(step & pmask) * rowlen;
+                    row[si] = node < 0 ? psi_now : psic[node * CT + si];     // Psi_all[m]  (:365)
+                    row[CT + si] = node < 0 ? y_now : ycand[node * CT + si]; // Y_all[m]    (:364)
+                    if (tid == 0) { row[2 * CT] = bc[48 + d]; row[2 * CT + 1] = bc[56 + d]; }
                 }
             }
-        } else if (dev_stream && !init && mcur + 2 < m_end) {
-            const int mm = mcur + 2;                                         // buffer released by step m
-            for (int i = s.tid - s.nstate; i < s.CTm; i += s.nthreads - s.nstate)
-                s.zb[(mm & 1) * s.CT + i] = dg_normal(sa.seed, sid, (uint32_t)mm, (uint32_t)i);
-            if (s.tid == s.nthreads - 1) s.zb[(mm & 1) * s.CT + s.CT - 1] = log(dg_uniform(sa.seed, sid, (uint32_t)mm));
+            if (s_act && (init || fin >= 0)) {
+                const int f0 = init ? 0 : fin;
+                y_now = ycand[f0 * CT + si];
+                psi_now = psic[f0 * CT + si];
+            }
+            bar_state(nstate);                                               // candidates may be overwritten now
+        } else if (!init && nd > 0) {
+            // ring entries of the steps just consumed are free: refill them RING steps ahead
+            produce_stream(dev_stream, min(m + RING, m_end), min(m + nd + RING, m_end), tid - nstate, nthreads - nstate,
+                           false, zring, dring, RING, CT, CTm, Tc, pfac, sqs, sa.seed, sid, dblk, ublk, m_start);
         }
-        if (init) continue;
-        if (pg_new < 0) {                                                    // trace pool exhausted (uniform)
+        if (init) { init = false; continue; }
+        m += nd;
+        if (nomem) {                                                         // trace pool exhausted (uniform)
             state = DICEGP_CHAIN_NOMEM_;
-            m_ret = mcur - 1;
-            m = mcur;
+            m_ret = m - 1;
             break;
         }
-        m = mcur + 1;
-        // convergence diagnostics (:369-391); rows [0, m) exclude the one just written
-        if (mcur >= initial && (mcur % gap) == 0) {
+        // convergence diagnostics (:369-391) after step m-1 if it is a check step; the rows
+        // [0, m-1) exclude the one just written
+        const int mlast = m - 1;
+        if (nd > 0 && mlast >= initial && (mlast % gap) == 0) {
             __syncthreads();
             DG_TICK(4);
-            const int conv = geweke_converged(s.gw, s.CTm, s.nwarps, s.warp, s.lane, tv, mcur);
+            const int conv = geweke_converged(gw, CTm, nwarps, warp, lane, tv, mlast);
             DG_TICK(5);
             if (conv) {
                 state = DICEGP_CHAIN_CONVERGED_;
-                m_ret = mcur;
+                m_ret = mlast;
                 break;
             }
         }
@@ -608,9 +691,9 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
 
     // ---- save state ------------------------------------------------------------------------
     __syncthreads();
-    if (s_act) { st[si] = y_now; st[s.CT + si] = psi_now; }
-    if (s.tid == 0) {
-        st[2 * s.CT] = P_now; st[2 * s.CT + 1] = L_now;
+    if (s_act && nd_j == 0) { st[si] = y_now; st[CT + si] = psi_now; }
+    if (tid == 0) {
+        st[2 * CT] = P_now; st[2 * CT + 1] = L_now;
         ct.m_next[chain] = m;
         ct.cnt[chain] = cnt;
         ct.flags[chain] = flags;

@@ -85,25 +85,31 @@ struct TraceView {
 // ---------------------------------------------------------------------------------------
 struct SmLayout {
     // offsets in doubles from the start of dynamic shared memory
-    int ytry, fsi, ex, gs, pr, qq, zb;                         // CT each (zb: 2*CT)
+    int ycand, psic, gs, ex, pr, qq;                           // J*CT each (J = 2^D - 1 candidates)
+    int ff;                                                    // CT*(J+1): f of all candidates, [t][k][j]
+    int zring, dring;                                          // 2*D*CT each: stream ring (z, delta + log u)
     int kinv, pfac;                                            // Tc*Tc each
     int ijs, jcon, sqs;                                        // C each
     int red, redi, redb, bc, gw, rel, seg, mbar;               // scratch
-    int w;                                                     // W (resident classes)
+    int w;                                                     // W (resident tiers)
     int total;                                                 // doubles without W
 };
 
-__host__ __device__ inline SmLayout dg_layout(int C, int Tc, int nwarps) {
+__host__ __device__ inline SmLayout dg_layout(int C, int Tc, int nwarps, int D) {
     SmLayout L;
+    const int J = (1 << D) - 1, JP = J + 1, RING = 2 * D;
     int CT = C * Tc, TT = Tc * Tc, o = 0;
-    L.ytry = o; o += CT;  L.fsi = o; o += CT;  L.ex = o; o += CT;  L.gs = o; o += CT;
-    L.pr = o; o += CT;    L.qq = o; o += CT;   L.zb = o; o += 2 * CT;
+    L.ycand = o; o += J * CT;  L.psic = o; o += J * CT;  L.gs = o; o += J * CT;  L.ex = o; o += J * CT;
+    L.pr = o; o += J * CT;     L.qq = o; o += J * CT;
+    o = (o + 1) & ~1;
+    L.ff = o; o += CT * JP;                    // 16-byte aligned rows of JP doubles
+    L.zring = o; o += RING * CT;  L.dring = o; o += RING * CT;
     L.kinv = o; o += TT;  L.pfac = o; o += TT;
     L.ijs = o; o += C;    L.jcon = o; o += C;  L.sqs = o; o += C;
-    L.red = o; o += DG_MAXWARPS;
-    L.redi = o; o += DG_MAXWARPS / 2;          // ints
+    L.red = o; o += J * DG_MAXWARPS;
+    L.redi = o; o += J * DG_MAXWARPS / 2 + 1;  // ints
     L.redb = o; o += DG_MAXWARPS / 2;          // unsigned
-    L.bc = o; o += 8;
+    L.bc = o; o += 64;
     L.gw = o; o += 2 * nwarps * DG_GW_COLS;
     L.rel = o; o += Tc + 2;                    // ints: rel roff[Tc+1], ncnt[Tc]
     L.seg = o; o += (3 * DG_MAXWARPS + 1) / 2 + 1;   // ints: up to 32 segments x (tt, first, stride)
@@ -172,6 +178,19 @@ __device__ __forceinline__ double dg_normal(uint64_t seed, int64_t sid, uint32_t
     sincospi(2.0 * u2, &s, &c);
     (void)s;
     return sqrt(-2.0 * log(u1)) * c;
+}
+// two normals from one Philox block (Box-Muller, sine and cosine branch)
+__device__ __forceinline__ void dg_normal_pair(uint64_t seed, int64_t sid, uint32_t step, uint32_t pair,
+                                               double &z0, double &z1) {
+    uint32_t o[4];
+    dg_philox(step, pair, (uint32_t)sid, (uint32_t)((uint64_t)sid >> 32),
+              (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    const double u1 = dg_u53(o[0], o[1]), u2 = dg_u53(o[2], o[3]);
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    const double r = sqrt(-2.0 * log(u1));
+    z0 = r * c;
+    z1 = r * s;
 }
 __device__ __forceinline__ double dg_uniform(uint64_t seed, int64_t sid, uint32_t step) {
     uint32_t o[4];

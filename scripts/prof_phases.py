@@ -1,4 +1,4 @@
-"""Per-phase cycle counts (needs the DG_PROFILE build: DICEGP_LIB=diceseq_b200/libdicegp_prof.so)."""
+"""Per-phase cycle counts (needs a DG_PROFILE build: DICEGP_LIB=diceseq_b200/libdicegp_prof_dN.so)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -13,11 +13,14 @@ def run(cfg, genes, M, initial, **kw):
     sys.stderr.flush()
     s.run(packed, M=M, initial=initial, gap=100, seed=1, summarize=False)
     st = s.stats
-    print("   kernel %.2f ms, %.3e evals/s" % (st["kernel_ms"], st["read_evals"] / st["kernel_ms"] * 1e3), flush=True)
+    print("   main kernel %.2f ms, %.3e evals/s" % (st["main_kernel_ms"], st["main_read_evals"] / st["main_kernel_ms"] * 1e3), flush=True)
 
-run("static", [0], 4000, 100000)
-run("static", range(4096), 3000, 1000)
-for C in (2, 4, 8):
-    run("timeseries", [0], 3000, 100000, C=C)
-for C in (2, 4, 8):
-    run("timeseries", range(296), 2000, 100000, C=C)
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "small"):
+    run("static", [0], 4000, 100000)
+    run("static", range(1184), 3000, 100000)
+if which in ("all", "big"):
+    for C in (2, 4, 8):
+        run("timeseries", range(148), 2000, 100000, C=C)
+    for C in (4, 8):
+        run("timeseries", range(592), 2000, 100000, C=C)
