@@ -27,12 +27,12 @@ constexpr int DICEGP_CHAIN_NOMEM_ = 3;
 // Persistent (queue != nullptr): blocks pull slots from an atomic counter until empty;
 // ids are sorted by decreasing cost so the heavy chains start first.
 #ifndef DG_LB_THREADS
-#define DG_LB_THREADS DG_MAXTHREADS      // 1024 threads/SM -> 64 registers per thread
+#define DG_LB_THREADS 512                // 512 threads/SM -> up to 128 registers per thread
 #endif
 #ifndef DG_SPEC_DEPTH
 #define DG_SPEC_DEPTH 2                  // MH steps decided per pass over W (speculation tree depth)
 #endif
-template <int KC, bool W_IN_SMEM>
+template <int KC, int WMODE>
 __global__ void __launch_bounds__(DG_LB_THREADS, 1)
 dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__restrict__ ids, int n_ids,
                     int n_steps, int use_tma, int *queue) {
@@ -47,7 +47,7 @@ dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__res
             __syncthreads();
         }
         if (slot >= n_ids) break;
-        dg::run_chain<KC, W_IN_SMEM, DG_SPEC_DEPTH>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma);
+        dg::run_chain<KC, WMODE, DG_SPEC_DEPTH>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma);
         __syncthreads();
         if (queue == nullptr) break;
     }
@@ -404,13 +404,13 @@ constexpr int kGroups = kTiers * kKinds;
 void launch_classes(const dicegp_ctx *c, LaunchClass out[kTiers]) {
     const size_t per_sm = 233472;  // 228 KB
     const int bps[4] = {8, 4, 2, 1};
-    const int thr[4] = {128, 256, 512, 1024};
+    const int thr[4] = {64, 128, 256, 512};
     for (int i = 0; i < 4; ++i) {
         size_t lim = per_sm / bps[i] - 1024;
         if (lim > c->smem_optin - c->static_smem) lim = c->smem_optin - c->static_smem;
         out[i] = {thr[i], lim, bps[i], true};
     }
-    out[4] = {256, 0, 4, false};
+    out[4] = {256, 0, 2, false};
     // development overrides: DICEGP_TIER_THREADS / DICEGP_TIER_BPS = five comma-separated ints
     const char *et = getenv("DICEGP_TIER_THREADS"), *eb = getenv("DICEGP_TIER_BPS");
     if (et) sscanf(et, "%d,%d,%d,%d,%d", &out[0].threads, &out[1].threads, &out[2].threads, &out[3].threads, &out[4].threads);
@@ -440,12 +440,9 @@ int64_t chain_wbytes(const dicegp_ctx *c, int chain) {
 
 inline int kind_of(int C) { return (C >= 2 && C <= 8) ? C - 1 : 0; }
 
-// threads a chain needs at least: its state warps (one lane per candidate node and latent
-// value) plus one likelihood warp
-inline int min_threads(int C, int Tc) {
-    const int J = (1 << DG_SPEC_DEPTH) - 1;
-    return ((J * C * Tc + 31) / 32) * 32 + 32;
-}
+// threads a chain needs at least: its state warps (one lane per latent value) plus one
+// likelihood warp
+inline int min_threads(int C, int Tc) { return ((C * Tc + 31) / 32) * 32 + 32; }
 
 int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain) {
     const dicegp_chain_desc &d = c->hdesc[chain];
@@ -460,15 +457,16 @@ int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain) {
 
 typedef void (*chain_kernel_t)(GeneTab, ChainTab, StreamArgs, const int32_t *, int, int, int, int *);
 chain_kernel_t chain_kernel_for(int kind, bool w_in_smem) {
+    // streamed W: staged through cp.async for compiled isoform counts, plain loads otherwise
     switch (kind * 2 + (w_in_smem ? 1 : 0)) {
-        case 0: return dicegp_chain_kernel<0, false>;   case 1: return dicegp_chain_kernel<0, true>;
-        case 2: return dicegp_chain_kernel<2, false>;   case 3: return dicegp_chain_kernel<2, true>;
-        case 4: return dicegp_chain_kernel<3, false>;   case 5: return dicegp_chain_kernel<3, true>;
-        case 6: return dicegp_chain_kernel<4, false>;   case 7: return dicegp_chain_kernel<4, true>;
-        case 8: return dicegp_chain_kernel<5, false>;   case 9: return dicegp_chain_kernel<5, true>;
-        case 10: return dicegp_chain_kernel<6, false>;  case 11: return dicegp_chain_kernel<6, true>;
-        case 12: return dicegp_chain_kernel<7, false>;  case 13: return dicegp_chain_kernel<7, true>;
-        case 14: return dicegp_chain_kernel<8, false>;  default: return dicegp_chain_kernel<8, true>;
+        case 0: return dicegp_chain_kernel<0, dg::W_DIRECT>;   case 1: return dicegp_chain_kernel<0, dg::W_RESIDENT>;
+        case 2: return dicegp_chain_kernel<2, dg::W_STAGED>;   case 3: return dicegp_chain_kernel<2, dg::W_RESIDENT>;
+        case 4: return dicegp_chain_kernel<3, dg::W_STAGED>;   case 5: return dicegp_chain_kernel<3, dg::W_RESIDENT>;
+        case 6: return dicegp_chain_kernel<4, dg::W_STAGED>;   case 7: return dicegp_chain_kernel<4, dg::W_RESIDENT>;
+        case 8: return dicegp_chain_kernel<5, dg::W_STAGED>;   case 9: return dicegp_chain_kernel<5, dg::W_RESIDENT>;
+        case 10: return dicegp_chain_kernel<6, dg::W_STAGED>;  case 11: return dicegp_chain_kernel<6, dg::W_RESIDENT>;
+        case 12: return dicegp_chain_kernel<7, dg::W_STAGED>;  case 13: return dicegp_chain_kernel<7, dg::W_RESIDENT>;
+        case 14: return dicegp_chain_kernel<8, dg::W_STAGED>;  default: return dicegp_chain_kernel<8, dg::W_RESIDENT>;
     }
 }
 
@@ -555,6 +553,12 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                 const dicegp_chain_desc &d = c->hdesc[id];
                 size_t need = fixed_smem_bytes(c->hC[d.gene], d.Tc, cls[tier].threads);
                 if (cls[tier].w_in_smem) need += (size_t)chain_wbytes(c, id);
+                else if (kind != 0) {
+                    // per likelihood warp: kStages x C x 32 lanes x 16 bytes of cp.async staging
+                    const int C = c->hC[d.gene];
+                    const int nwl = cls[tier].threads / 32 - (C * d.Tc + 31) / 32;
+                    need += (size_t)nwl * dg::kStages * C * 512;
+                }
                 smem = std::max(smem, need);
             }
             smem = (smem + 127) & ~(size_t)127;
@@ -659,8 +663,8 @@ int dicegp_create(int device, dicegp_ctx **out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     {
         cudaFuncAttributes fa0, fa1;
-        if (cudaFuncGetAttributes(&fa0, dicegp_chain_kernel<0, false>) != cudaSuccess ||
-            cudaFuncGetAttributes(&fa1, dicegp_chain_kernel<0, true>) != cudaSuccess) {
+        if (cudaFuncGetAttributes(&fa0, dicegp_chain_kernel<0, dg::W_DIRECT>) != cudaSuccess ||
+            cudaFuncGetAttributes(&fa1, dicegp_chain_kernel<0, dg::W_RESIDENT>) != cudaSuccess) {
             g_last_error = std::string("kernel image not loadable on this device: ") + cudaGetErrorString(cudaGetLastError());
             delete c;
             return DICEGP_ERR_CUDA;

@@ -34,54 +34,126 @@ __device__ __forceinline__ double dg_mant(double x, int hi) {
     return __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
 }
 
-// One likelihood segment: pairs p = p0, p0+stride, ... of one time point, J candidates.
+// How a likelihood warp gets at W:
+//   W_RESIDENT  the chain's W sits in shared memory (staged once per launch by a TMA bulk copy)
+//   W_STAGED    W streams from L2/HBM through a per-warp ring of cp.async stages (each lane
+//               copies exactly the 16-byte words it will consume: no barrier, deep prefetch)
+//   W_DIRECT    plain global loads (isoform counts too large for the staging ring)
+enum { W_RESIDENT = 0, W_STAGED = 1, W_DIRECT = 2 };
+constexpr int kStages = 4;
+
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dg_smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Likelihood pass of one warp.  The chain's reads are cut into ITEMS of 32 consecutive read
+// pairs of one time point (cum[t] = first item of time t); item q belongs to warp q % NWL.
 //   x_n^(j) = sum_k W[n,k] f^(j)[k]                            model_GP.py:338
-// W block: isoform-major, row k = npairs double2 (two reads per 16-byte load; consecutive
-// lanes take consecutive pairs: conflict-free LDS.128 / coalesced LDG.128).  f of the J
-// candidates sits in shared memory as ff[k][JP] and is read as broadcast LDS.128.
-// prod_n x_n is carried per candidate as a mantissa product and an exponent sum; anything
-// that is not a positive normal double raises `bad` (the round is then redone with logs).
-template <int KC, int J, bool LOGPATH>
-__device__ __forceinline__ void lik_segment(const double2 *__restrict__ Wt, int npairs, int n, int C,
-                                            const double *ffcol, int p0, int stride, double (&mm)[J],
-                                            int (&ee)[J], unsigned &bad, double (&ls)[J]) {
+// W block of a time point: isoform-major, row k = npairs double2 (two reads per 16-byte
+// word; consecutive lanes take consecutive words: conflict-free LDS.128 / coalesced
+// LDG.128).  f of the J candidates sits in shared memory as ff[t][k][JP] and is read as
+// broadcast LDS.128.  prod_n x_n is carried per candidate as a mantissa product and an
+// exponent sum; anything that is not a positive normal double raises `bad` (the round is
+// then redone with real logarithms, LOGPATH).
+template <int KC, int J, int WMODE, bool LOGPATH>
+__device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, int Tc, const int *rel, const int *ncnt,
+                                         const int *cum, const double *ff, double *stage, int lane, int wl, int NWL,
+                                         double (&mm)[J], int (&ee)[J], unsigned &bad, double (&ls)[J]) {
     constexpr int JP = J + 1;
-    int it = 0;
-    for (int p = p0; p < npairs; p += stride) {
-        double x0[J], x1[J];
+    const int nitems = cum[Tc];
+    const int kmax = KC > 0 ? KC : C;
+    double2 *mystage = reinterpret_cast<double2 *>(stage) + lane;     // [stage][k][32 lanes]
+    int qi = wl, tti = 0;                                             // issue cursor (W_STAGED)
+    auto issue = [&](int slot) {
+        if (qi < nitems) {
+            while (qi >= cum[tti + 1]) ++tti;
+            const int r0 = rel[tti], npairs = (rel[tti + 1] - r0) >> 1;
+            const int p = (qi - cum[tti]) * 32 + lane;
+            if (p < npairs) {
+                const double2 *src = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0) + p;
 #pragma unroll
-        for (int j = 0; j < J; ++j) { x0[j] = 0.0; x1[j] = 0.0; }
-        const int kmax = KC > 0 ? KC : C;
+                for (int k = 0; k < kmax; ++k) cp_async16(mystage + (slot * kmax + k) * 32, src + (size_t)k * npairs);
+            }
+            qi += NWL;
+        }
+        cp_async_commit();
+    };
+    if (WMODE == W_STAGED) {
 #pragma unroll
-        for (int k = 0; k < kmax; ++k) {
-            const double2 w = Wt[(size_t)k * npairs + p];
-            const double2 *f2 = reinterpret_cast<const double2 *>(ffcol + k * JP);
-            double fj[JP];
+        for (int s = 0; s < kStages - 1; ++s) issue(s);
+    }
+    constexpr bool FREG = (KC > 0 && KC * J <= 24);                   // f of the time point held in registers
+    constexpr int FR = FREG ? KC : 1;
+    int it = 0, q = wl;
+    for (int tt = 0; tt < Tc; ++tt) {
+        const int c0 = cum[tt], c1 = cum[tt + 1];
+        if (q >= c1) continue;
+        const int r0 = rel[tt], npairs = (rel[tt + 1] - r0) >> 1, n = ncnt[tt];
+        const double2 *Wt0 = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0) + lane;
+        const double *ffcol = ff + (size_t)tt * C * JP;
+        double fr[FR][J];
+        if (FREG) {
 #pragma unroll
-            for (int q = 0; q < JP / 2; ++q) { const double2 t = f2[q]; fj[2 * q] = t.x; fj[2 * q + 1] = t.y; }
+            for (int k = 0; k < FR; ++k) {
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                x0[j] = fma(w.x, fj[j], x0[j]);
-                x1[j] = fma(w.y, fj[j], x1[j]);
+                for (int j = 0; j < J; ++j) fr[k][j] = ffcol[k * JP + j];
             }
         }
-        const bool v1 = (2 * p + 1) < n;              // the pad slot of an odd block
-        if (LOGPATH) {
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                ls[j] += log(x0[j]);
-                if (v1) ls[j] += log(x1[j]);
+        for (; q < c1; q += NWL, ++it) {
+            const int p = (q - c0) * 32 + lane;
+            if (WMODE == W_STAGED) {
+                issue((it + kStages - 1) & (kStages - 1));
+                cp_async_wait<kStages - 1>();
             }
-        } else {
+            if (p < npairs) {
+                const double2 *Wt = Wt0 + (q - c0) * 32;
+                const double2 *st = mystage + ((it & (kStages - 1)) * kmax) * 32;
+                double x0[J], x1[J];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const double y1 = v1 ? x1[j] : 1.0;
-                const int h0 = __double2hiint(x0[j]), h1 = __double2hiint(y1);
-                bad |= (((unsigned)(h0 - 0x00100000) >= 0x7fe00000u) || ((unsigned)(h1 - 0x00100000) >= 0x7fe00000u)) ? 1u : 0u;
-                ee[j] += (h0 >> 20) + (h1 >> 20) - 2046;
-                mm[j] *= dg_mant(x0[j], h0) * dg_mant(y1, h1);
+                for (int j = 0; j < J; ++j) { x0[j] = 0.0; x1[j] = 0.0; }
+#pragma unroll
+                for (int k = 0; k < kmax; ++k) {
+                    const double2 w = (WMODE == W_STAGED) ? st[k * 32] : Wt[(size_t)k * npairs];
+                    if (FREG) {
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            x0[j] = fma(w.x, fr[k < FR ? k : 0][j], x0[j]);
+                            x1[j] = fma(w.y, fr[k < FR ? k : 0][j], x1[j]);
+                        }
+                    } else {
+                        const double2 *f2 = reinterpret_cast<const double2 *>(ffcol + k * JP);
+                        double fj[JP];
+#pragma unroll
+                        for (int u = 0; u < JP / 2; ++u) { const double2 t = f2[u]; fj[2 * u] = t.x; fj[2 * u + 1] = t.y; }
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            x0[j] = fma(w.x, fj[j], x0[j]);
+                            x1[j] = fma(w.y, fj[j], x1[j]);
+                        }
+                    }
+                }
+                const bool v1 = (2 * p + 1) < n;              // the pad slot of an odd block
+                if (LOGPATH) {
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        ls[j] += log(x0[j]);
+                        if (v1) ls[j] += log(x1[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        const double y1 = v1 ? x1[j] : 1.0;
+                        const int h0 = __double2hiint(x0[j]), h1 = __double2hiint(y1);
+                        bad |= (((unsigned)(h0 - 0x00100000) >= 0x7fe00000u) || ((unsigned)(h1 - 0x00100000) >= 0x7fe00000u)) ? 1u : 0u;
+                        ee[j] += (h0 >> 20) + (h1 >> 20) - 2046;
+                        mm[j] *= dg_mant(x0[j], h0) * dg_mant(y1, h1);
+                    }
+                }
             }
-            if (((++it) & 255) == 0) {                 // keep the running products in range
+            if (!LOGPATH && (it & 255) == 255) {               // keep the running products in range
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     const int g = __double2hiint(mm[j]);
@@ -91,26 +163,21 @@ __device__ __forceinline__ void lik_segment(const double2 *__restrict__ Wt, int 
             }
         }
     }
+    if (WMODE == W_STAGED) cp_async_wait<0>();
 }
 
 // Slow path (some x_n is 0 / negative / non-finite): the same sums with real logarithms so
 // that -inf and NaN propagate like np.log(...).sum() does (model_GP.py:344).
-template <int KC, int J>
-__device__ __noinline__ void lik_warp_pass_log(const double *Wc, const int *seg, const int *rel, const int *ncnt,
-                                               const double *ff, double *red, int C, int NWL, int lane, int wl,
-                                               int nseg) {
-    constexpr int JP = J + 1;
+template <int KC, int J, int WMODE>
+__device__ __noinline__ void lik_warp_pass_log(const double *Wc, const int *rel, const int *ncnt, const int *cum,
+                                               const double *ff, double *stage, double *red, int C, int Tc, int NWL,
+                                               int lane, int wl) {
     double mm[J], ls[J];
     int ee[J];
     unsigned bad = 0u;
 #pragma unroll
     for (int j = 0; j < J; ++j) { mm[j] = 1.0; ls[j] = 0.0; ee[j] = 0; }
-    for (int sg = wl; sg < nseg; sg += NWL) {
-        const int tt = seg[3 * sg], first = seg[3 * sg + 1], stride = seg[3 * sg + 2];
-        const int r0 = rel[tt], npairs = (rel[tt + 1] - r0) >> 1;
-        const double2 *Wt = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0);
-        lik_segment<KC, J, true>(Wt, npairs, ncnt[tt], C, ff + (size_t)tt * C * JP, first + lane, stride, mm, ee, bad, ls);
-    }
+    lik_pass<KC, J, WMODE, true>(Wc, C, Tc, rel, ncnt, cum, ff, stage, lane, wl, NWL, mm, ee, bad, ls);
 #pragma unroll
     for (int j = 0; j < J; ++j) {
         double v = ls[j];
@@ -183,31 +250,6 @@ __device__ __noinline__ int geweke_converged(double *gw, int CTm, int nwarps, in
     return __syncthreads_and(ok);
 }
 
-// Which likelihood warp reads which slice: segment = (time point, first pair, stride).
-// Warps are dealt to time points in proportion to their read pairs; with fewer warps
-// than time points every time point is one segment and warps take several.
-__device__ __noinline__ int build_segments(int *seg, const int *rel, int Tc, int NWL) {
-    if (Tc >= NWL) {
-        for (int t = 0; t < Tc; ++t) { seg[3 * t] = t; seg[3 * t + 1] = 0; seg[3 * t + 2] = 32; }
-        return Tc;
-    }
-    int nw[DG_MAXT];
-    for (int t = 0; t < Tc; ++t) nw[t] = 1;
-    for (int w = Tc; w < NWL; ++w) {
-        int best = 0;
-        double load = -1.0;
-        for (int t = 0; t < Tc; ++t) {
-            const double l = (double)(rel[t + 1] - rel[t]) / (double)nw[t];
-            if (l > load) { load = l; best = t; }
-        }
-        ++nw[best];
-    }
-    int k = 0;
-    for (int t = 0; t < Tc; ++t)
-        for (int j = 0; j < nw[t]; ++j) { seg[3 * k] = t; seg[3 * k + 1] = 32 * j; seg[3 * k + 2] = 32 * nw[t]; ++k; }
-    return k;
-}
-
 // Out-of-line copies of the long math routines used on the round loop: the loop body has
 // to stay small enough for the instruction cache (the serial part runs in one warp, which
 // cannot hide instruction-fetch latency).
@@ -274,7 +316,7 @@ __device__ __noinline__ long long trace_page(int64_t *ptab, int step, int pshift
 // ---------------------------------------------------------------------------------------
 // one chain, up to n_steps steps.  `slot` indexes the host stream blocks.
 // ---------------------------------------------------------------------------------------
-template <int KC, bool W_IN_SMEM, int D>
+template <int KC, int WMODE, int D>
 __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArgs &sa, int chain,
                           int slot, int n_steps, double *smem, int use_tma) {
     constexpr int J = (1 << D) - 1;
@@ -288,7 +330,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     const int C = KC > 0 ? KC : gt.C[g];
     const int Tc = ct.Tc[chain], T = gt.T;
     const int CT = C * Tc, CTm = (C - 1) * Tc;
-    const int S = (J * CT + 31) >> 5, nstate = S << 5, NWL = nwarps - S;
+    const int S = (CT + 31) >> 5, nstate = S << 5, NWL = nwarps - S;
     const SmLayout L = dg_layout(C, Tc, nwarps, D);
     double *ycand = smem + L.ycand, *psic = smem + L.psic, *gs = smem + L.gs, *ex = smem + L.ex;
     double *pr = smem + L.pr, *qq = smem + L.qq, *ff = smem + L.ff, *zring = smem + L.zring, *dring = smem + L.dring;
@@ -297,7 +339,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     int *redi = reinterpret_cast<int *>(smem + L.redi);
     unsigned *redb = reinterpret_cast<unsigned *>(smem + L.redb);
     int *rel = reinterpret_cast<int *>(smem + L.rel), *ncnt = rel + (Tc + 1);
-    int *seg = reinterpret_cast<int *>(smem + L.seg);
+    int *cum = reinterpret_cast<int *>(smem + L.seg);      // first 32-pair item of every time point
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + L.mbar);
     double *Wsm = smem + L.w;
     const double prior_const = ct.prior_const[chain];
@@ -309,7 +351,9 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     const int r_total = roff[Tc] - r_first;
     const double *Wg = gt.W + gt.woff[g] + (size_t)C * r_first;
     const size_t wbytes = (size_t)C * r_total * sizeof(double);
+    constexpr bool W_IN_SMEM = (WMODE == W_RESIDENT);
     const double *Wc = W_IN_SMEM ? Wsm : Wg;
+    double *stage = Wsm + (size_t)(wl > 0 ? wl : 0) * kStages * C * 64;   // W_STAGED: per-warp cp.async ring
 
     // ---- stage W (TMA bulk copy, asynchronous) and the small per-chain constants --------
     if (W_IN_SMEM) {
@@ -370,23 +414,27 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     const int64_t sid = ct.stream_id ? ct.stream_id[chain] : (int64_t)chain;
     const bool dev_stream = sa.mode != 0;
 
-    // ---- state lanes: lane s = node*CT + (c*Tc + t) ----------------------------------------
-    const bool s_act = is_state && tid < J * CT;          // owns a latent value of a candidate node
-    const int nd_j = s_act ? tid / CT : 0;                // candidate node (heap order)
-    const int si = s_act ? tid - nd_j * CT : 0;           // c*Tc + t
+    // ---- state lanes: one thread per latent value (c, t); the J candidate nodes of a round
+    //      are walked in registers (independent exp / divide chains overlap) -------------------
+    const bool s_act = is_state && tid < CT;              // owns a latent value
+    const int si = s_act ? tid : 0;                       // c*Tc + t
     const int sc = si / Tc, stt = si - sc * Tc;
     const bool s_free = s_act && sc < C - 1;              // value is sampled (c < C-1)
-    int nd_depth = 0;                                     // depth of the node = step offset it proposes
-    while ((2 << nd_depth) <= nd_j + 1) ++nd_depth;
-    const int nd_path = (nd_j + 1) - (1 << nd_depth);     // edge bits root->node, MSB first: 1 = accepted parent
-    double y_now = 0.0, psi_now = 0.0;                    // replicated over the J node groups
+    double y_now = 0.0, psi_now = 0.0;
     double P_now = 0.0, L_now = 0.0;                      // thread 0
     int cnt = 0, flags = 0;
     if (tid == 0) { cnt = ct.cnt[chain]; flags = ct.flags[chain]; }
     const double len_own = s_act ? gt.len[gt.lenoff[g] + (size_t)(t0 + stt) * C + sc] : 0.0;
+    const double *kinv_col = kinv + stt;                  // column t of K^-1
+    double *ff_own = ff + (stt * C + sc) * JP;            // f of this (t, c), all candidates
+    const double *y0p = ct.y0_off[chain] >= 0 ? ct.pool + ct.y0_off[chain] : nullptr;
 
     __syncthreads();                                      // rel / ncnt visible
-    if (tid == 0) bc[15] = (double)build_segments(seg, rel, Tc, NWL);
+    if (tid == 0) {
+        int a = 0;
+        for (int t = 0; t < Tc; ++t) { cum[t] = a; a += (((rel[t + 1] - rel[t]) >> 1) + 31) >> 5; }
+        cum[Tc] = a;
+    }
     if (m > 0 && s_act) { y_now = st[si]; psi_now = st[CT + si]; }
     if (m > 0 && tid == 0) { P_now = st[2 * CT]; L_now = st[2 * CT + 1]; }
     if (W_IN_SMEM && use_tma && wbytes > 0) {
@@ -400,7 +448,6 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         }
     }
     __syncthreads();
-    const int nseg = (int)bc[15];
 
     const int m_start = m;
     const int m_end = (m_start + n_steps < M) ? (m_start + n_steps) : M;
@@ -419,46 +466,57 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
 #endif
 
     bool init = (m == 0);                                 // evaluate the start value first (model_GP.py:275-292)
+    // next convergence-check step at or after m (m >= initial and m % gap == 0)
+    int next_check = m > initial ? m : initial;
+    next_check += (gap - next_check % gap) % gap;
+    int rbase = m % RING;                                 // ring slot of step m
     while (m < m_end || init) {
         // steps this round may commit: up to D, not past the chunk, not past a check step
-        int nd_max = 0;
-        if (!init) {
-            int mc = m > initial ? m : initial;
-            mc += (gap - mc % gap) % gap;                 // next step with m >= initial and m % gap == 0
-            nd_max = min(D, min(m_end - m, mc - m + 1));
-        }
+        const int nd_max = init ? 0 : min(D, min(m_end - m, next_check - m + 1));
         // ================= S phase (state warps): candidates -> f =================
-        double y_c = 0.0, base_c = 0.0, e_c = 1.0, g_c = 0.0, psi_c = 0.0;
+        double yj[J], bj[J], ej[J], gj[J];
         if (is_state) {
             if (s_act) {
                 if (init) {
-                    const double *y0 = ct.y0_off[chain] >= 0 ? ct.pool + ct.y0_off[chain] : nullptr;
-                    y_c = y0 ? y0[si] : 0.0;                                 // Y_now = Ymean (:275)
-                    base_c = y_c;
-                } else if (s_free) {
-                    // state before this node proposes: Y_now moved through its accepted ancestors
-                    double cur = y_now;
+                    const double v = y0p ? y0p[si] : 0.0;                    // Y_now = Ymean (:275)
 #pragma unroll
-                    for (int i = 0; i < D - 1; ++i) {
-                        if (i < nd_depth && i < nd_max && ((nd_path >> (nd_depth - 1 - i)) & 1))
-                            cur = dring[((m + i) % RING) * CT + si] + cur;
+                    for (int j = 0; j < J; ++j) { yj[j] = v; bj[j] = v; }
+                } else if (s_free) {
+                    double dl[D];                                            // increments of steps m .. m+D-1
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        int sl = rbase + d;
+                        if (sl >= RING) sl -= RING;
+                        dl[d] = d < nd_max ? dring[sl * CT + si] : 0.0;
                     }
-                    const double dl = (nd_depth < nd_max) ? dring[((m + nd_depth) % RING) * CT + si] : 0.0;
-                    y_c = dl + cur;                                          // (:329) numpy adds the mean last
-                    base_c = cur;
-                }                                                            // else Y_try[C-1,:] stays 0 (:295)
-                e_c = exp(y_c);
-                g_c = len_own * e_c;
-                ycand[tid] = y_c;
-                ex[tid] = e_c;
-                gs[tid] = g_c;
+                    // node j (heap order): state before it proposes = Y_now moved through its accepted
+                    // ancestors; Y_try = delta + that state (:329, numpy adds the mean last)
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        const int dep = (j >= 3) ? 2 : (j >= 1 ? 1 : 0);
+                        if (j == 0) bj[j] = y_now;
+                        else bj[j] = (j & 1) ? bj[(j - 1) / 2] : yj[(j - 1) / 2];   // odd = parent rejected
+                        yj[j] = dl[dep] + bj[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < J; ++j) { yj[j] = 0.0; bj[j] = 0.0; }    // Y_try[C-1,:] stays 0 (:295)
+                }
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    ej[j] = exp(yj[j]);
+                    gj[j] = len_own * ej[j];
+                    ycand[j * CT + si] = yj[j];
+                    ex[j * CT + si] = ej[j];
+                    gs[j * CT + si] = gj[j];
+                }
             }
             bar_state(nstate);
             if (s_act) {
                 // fsi = len*psi / sum(len*psi) with psi = e/sum(e): the common 1/sum(e) cancels
                 // (model_GP.py:335-337; one division on the critical path instead of two)
-                const double sg = dg_np_sum(gs + nd_j * CT + stt, C, Tc);
-                ff[(stt * C + sc) * JP + nd_j] = g_c / sg;
+#pragma unroll
+                for (int j = 0; j < J; ++j) ff_own[j] = gj[j] / dg_np_sum(gs + j * CT + stt, C, Tc);
             }
         }
         __syncthreads();                                                     // B1: f ready
@@ -470,17 +528,12 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             unsigned bad = 0u;
 #pragma unroll
             for (int j = 0; j < J; ++j) { mm[j] = 1.0; ee[j] = 0; lsd[j] = 0.0; }
-            for (int sg = wl; sg < nseg; sg += NWL) {
-                const int tt = seg[3 * sg], first = seg[3 * sg + 1], stride = seg[3 * sg + 2];
-                const int r0 = rel[tt], npairs = (rel[tt + 1] - r0) >> 1;
-                const double2 *Wt = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0);
-                lik_segment<KC, J, false>(Wt, npairs, ncnt[tt], C, ff + (size_t)tt * C * JP, first + lane, stride, mm, ee, bad, lsd);
+            lik_pass<KC, J, WMODE, false>(Wc, C, Tc, rel, ncnt, cum, ff, stage, lane, wl, NWL, mm, ee, bad, lsd);
 #pragma unroll
-                for (int j = 0; j < J; ++j) {                                // a warp walking many segments stays in range
-                    const int gg = __double2hiint(mm[j]);
-                    ee[j] += (gg >> 20) - 1023;
-                    mm[j] = dg_mant(mm[j], gg);
-                }
+            for (int j = 0; j < J; ++j) {
+                const int gg = __double2hiint(mm[j]);
+                ee[j] += (gg >> 20) - 1023;
+                mm[j] = dg_mant(mm[j], gg);
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -502,31 +555,46 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             }
         } else {
             if (s_act) {
-                const double se = dg_np_sum(ex + nd_j * CT + stt, C, Tc);
-                psi_c = e_c / se;                                            // (:335)
-                psic[tid] = psi_c;
+#pragma unroll
+                for (int j = 0; j < J; ++j) psic[j * CT + si] = ej[j] / dg_np_sum(ex + j * CT + stt, C, Tc);   // (:335)
             }
             // GP prior (:332) and proposal density (:330-331): x K^-1 x as (x K^-1)[t] * x[t]
             if (s_free) {
-                const double *yc = ycand + nd_j * CT + sc * Tc;
-                double r = 0.0;
-                for (int j = 0; j < Tc; ++j) r = fma(yc[j], kinv[j * Tc + stt], r);
-                pr[tid] = r * y_c;
-                qq[tid] = base_c - y_c;                                      // d = Y_now - Y_try
+                double r[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) r[j] = 0.0;
+                for (int t2 = 0; t2 < Tc; ++t2) {
+                    const double kv = kinv_col[t2 * Tc];
+#pragma unroll
+                    for (int j = 0; j < J; ++j) r[j] = fma(ycand[j * CT + sc * Tc + t2], kv, r[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    pr[j * CT + si] = r[j] * yj[j];
+                    qq[j * CT + si] = bj[j] - yj[j];                         // d = Y_now - Y_try
+                }
             }
             bar_state(nstate);
-            double qpart = 0.0;
+            double qpart[J];
             if (s_free) {
-                const double *dc = qq + nd_j * CT + sc * Tc;
-                double dq = 0.0;
-                for (int j = 0; j < Tc; ++j) dq = fma(dc[j], kinv[j * Tc + stt], dq);
-                qpart = dq * (base_c - y_c);
+#pragma unroll
+                for (int j = 0; j < J; ++j) qpart[j] = 0.0;
+                for (int t2 = 0; t2 < Tc; ++t2) {
+                    const double kv = kinv_col[t2 * Tc];
+#pragma unroll
+                    for (int j = 0; j < J; ++j) qpart[j] = fma(qq[j * CT + sc * Tc + t2], kv, qpart[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < J; ++j) qpart[j] *= (bj[j] - yj[j]);
             }
             bar_state(nstate);                                               // everyone has read qq
-            if (s_free) qq[tid] = qpart;
+            if (s_free) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) qq[j * CT + si] = qpart[j];
+            }
             bar_state(nstate);
-            if (tid < J * (C - 1)) {                                         // lane (node, c): sums over t
-                const int jn = tid / (C - 1), c = tid - jn * (C - 1);
+            for (int q = tid; q < J * (C - 1); q += nstate) {                // (node, c): sums over t
+                const int jn = q / (C - 1), c = q - jn * (C - 1);
                 const double *prc = pr + jn * CT + c * Tc, *qc = qq + jn * CT + c * Tc;
                 double a = 0.0, b = 0.0;
                 for (int t = 0; t < Tc; ++t) { a += prc[t]; b += qc[t]; }
@@ -534,11 +602,11 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                 ex[jn * CT + c] = jcon[c] - (b * ijs[c]) / 2.0;
             }
             bar_state(nstate);
-            if (tid < J) {
+            for (int q = tid; q < J; q += nstate) {
                 double prior = 0.0, Q = 0.0;                                 // c ascending (:312-332)
-                for (int c = 0; c < C - 1; ++c) { prior += gs[tid * CT + c]; Q += ex[tid * CT + c]; }
-                bc[16 + tid] = prior;
-                bc[16 + J + tid] = init ? 0.0 : Q;
+                for (int c = 0; c < C - 1; ++c) { prior += gs[q * CT + c]; Q += ex[q * CT + c]; }
+                bc[16 + q] = prior;
+                bc[16 + J + q] = init ? 0.0 : Q;
             }
         }
         DG_TICK(1);
@@ -607,7 +675,9 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                                 for (int j = 1; j < J; ++j) if (j == node) likn = lik[j];
                                 const double P_try = priorn + likn;
                                 const double a = ((P_try + Q) - P_now) - Q;
-                                const double lu = dring[((m + d) % RING) * CT + CT - 1];
+                                int sl = rbase + d;
+                                if (sl >= RING) sl -= RING;
+                                const double lu = dring[sl * CT + CT - 1];
                                 const bool acc = (a >= 0.0) || (lu < a);     // NaN a: both false
                                 if (!isfinite(P_try)) flags |= 1;
                                 if (acc) { ++cnt; P_now = P_try; L_now = likn; cur = node; }
@@ -626,7 +696,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             __syncthreads();                                                 // B3: decisions (or redo request)
             redo = bc[3] != 0.0;
             if (redo) {                                                      // rare: some x_n was not a positive normal
-                if (!is_state) lik_warp_pass_log<KC, J>(Wc, seg, rel, ncnt, ff, red, C, NWL, lane, wl, nseg);
+                if (!is_state) lik_warp_pass_log<KC, J, WMODE>(Wc, rel, ncnt, cum, ff, stage, red, C, Tc, NWL, lane, wl);
                 __syncthreads();
             }
         } while (redo);
@@ -636,7 +706,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         const int fin = (int)bc[5];
         const bool nomem = bc[6] != 0.0;
         if (is_state) {
-            if (s_act && nd_j == 0) {                                        // primary lanes write the rows
+            if (s_act) {
                 for (int d = 0; d < nd; ++d) {
                     const int node = (int)bc[40 + d];
                     const int step = m + d;
@@ -645,11 +715,11 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                     row[CT + si] = node < 0 ? y_now : ycand[node * CT + si]; // Y_all[m]    (:364)
                     if (tid == 0) { row[2 * CT] = bc[48 + d]; row[2 * CT + 1] = bc[56 + d]; }
                 }
-            }
-            if (s_act && (init || fin >= 0)) {
-                const int f0 = init ? 0 : fin;
-                y_now = ycand[f0 * CT + si];
-                psi_now = psic[f0 * CT + si];
+                if (init || fin >= 0) {
+                    const int f0 = init ? 0 : fin;
+                    y_now = ycand[f0 * CT + si];
+                    psi_now = psic[f0 * CT + si];
+                }
             }
             bar_state(nstate);                                               // candidates may be overwritten now
         } else if (!init && nd > 0) {
@@ -659,6 +729,8 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         }
         if (init) { init = false; continue; }
         m += nd;
+        rbase += nd;
+        if (rbase >= RING) rbase -= RING;
         if (nomem) {                                                         // trace pool exhausted (uniform)
             state = DICEGP_CHAIN_NOMEM_;
             m_ret = m - 1;
@@ -677,6 +749,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                 m_ret = mlast;
                 break;
             }
+            next_check += gap;
         }
         DG_TICK(4);
     }
@@ -691,7 +764,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
 
     // ---- save state ------------------------------------------------------------------------
     __syncthreads();
-    if (s_act && nd_j == 0) { st[si] = y_now; st[CT + si] = psi_now; }
+    if (s_act) { st[si] = y_now; st[CT + si] = psi_now; }
     if (tid == 0) {
         st[2 * CT] = P_now; st[2 * CT + 1] = L_now;
         ct.m_next[chain] = m;

@@ -112,7 +112,7 @@ __host__ __device__ inline SmLayout dg_layout(int C, int Tc, int nwarps, int D) 
     L.bc = o; o += 64;
     L.gw = o; o += 2 * nwarps * DG_GW_COLS;
     L.rel = o; o += Tc + 2;                    // ints: rel roff[Tc+1], ncnt[Tc]
-    L.seg = o; o += (3 * DG_MAXWARPS + 1) / 2 + 1;   // ints: up to 32 segments x (tt, first, stride)
+    L.seg = o; o += (DG_MAXT + 2) / 2 + 1;     // ints: first 32-pair item of each time point
     L.mbar = o; o += 2;
     o = (o + 15) & ~15;                         // 128-byte align W
     L.w = o;
