@@ -254,6 +254,12 @@ def run_ours(args, wl):
     sampler.ctx.timer_start()
     for k in range(args.steps):
         res = sampler.sample(seed=k, **kw)
+        if rank == 0:
+            st_ = sampler.stats
+            print("[bench] resident step %d: prerun %.1f ms (%d launches), main %.1f ms (%d launches), summary %.1f ms, "
+                  "total sample() %.1f ms" % (k, st_["prerun_kernel_ms"], st_["prerun_launches"], st_["main_kernel_ms"],
+                                               st_["main_launches"], st_.get("summary_ms", 0.0), st_.get("sample_ms", 0.0)),
+                  file=sys.stderr)
         evals += sampler.stats["read_evals"]
         genes_done += G
         main_ms += sampler.stats["main_kernel_ms"]

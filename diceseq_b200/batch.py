@@ -151,6 +151,8 @@ class BatchSampler:
     def sample(self, X=None, theta1=3.0, theta2=None, M=20000, initial=1000, gap=100, seed=0,
                gene_ids=None, stream="device", keep_trace=False, summarize=True):
         """Pre-runs -> jump variance -> joint chains -> summaries for the uploaded genes."""
+        import time as _time
+        _t0 = _time.perf_counter()
         ctx, packed = self.ctx, self.packed
         G, T = packed.G, packed.T
         X = np.arange(T) if X is None else np.asarray(X)
@@ -198,9 +200,12 @@ class BatchSampler:
                               "use smaller batches" % int((st["state"] == _lib.CHAIN_NOMEM).sum()))
         res = BatchResult(packed.n_iso, T, st, var)
         if summarize:
+            _t1 = _time.perf_counter()
             res.psi_mean, res.psi_ci, res.lik_marg, res.off = ctx.posterior_summary(flat=True)
+            self.stats["summary_ms"] = (_time.perf_counter() - _t1) * 1e3
         if keep_trace:
             res.traces = [ctx.download_trace(g, int(st["n_rows"][g])) for g in range(G)]
+        self.stats["sample_ms"] = (_time.perf_counter() - _t0) * 1e3
         return res
 
     def run(self, packed, **kw):

@@ -194,6 +194,7 @@ __device__ __noinline__ void lik_warp_pass_log(const double *Wc, const int *rel,
 // (coalesced), warps walk rows.  Returns 1 to every thread when all |Z| <= 2.
 // ---------------------------------------------------------------------------------------
 __device__ __noinline__ int geweke_converged(double *gw, int CTm, int nwarps, int warp, int lane, TraceView tv, int m) {
+    const int GC = CTm < DG_GW_COLS ? (CTm > 0 ? CTm : 1) : DG_GW_COLS;   // scratch columns per warp
     const int nA = (int)(0.1 * (double)m);
     const int iB = (int)(0.5 * (double)m);
     const int nB = m - iB;
@@ -201,19 +202,20 @@ __device__ __noinline__ int geweke_converged(double *gw, int CTm, int nwarps, in
     for (int c0 = 0; c0 < CTm; c0 += DG_GW_COLS) {
         const int col = c0 + lane;
         const bool act = col < CTm;
-        double *gA = gw, *gB = gw + nwarps * DG_GW_COLS;
+        double *gA = gw, *gB = gw + nwarps * GC;
         double sa = 0.0, sb = 0.0;
         if (act) {
             for (int r = warp; r < nA; r += nwarps) sa += __ldcg(tv.row(r) + col);
             for (int r = iB + warp; r < m; r += nwarps) sb += __ldcg(tv.row(r) + col);
         }
-        gA[warp * DG_GW_COLS + lane] = sa;
-        gB[warp * DG_GW_COLS + lane] = sb;
+        if (lane < GC) { gA[warp * GC + lane] = sa; gB[warp * GC + lane] = sb; }
         __syncthreads();
         double meanA = 0.0, meanB = 0.0;
-        for (int w = 0; w < nwarps; ++w) {
-            meanA += gA[w * DG_GW_COLS + lane];
-            meanB += gB[w * DG_GW_COLS + lane];
+        if (lane < GC) {
+            for (int w = 0; w < nwarps; ++w) {
+                meanA += gA[w * GC + lane];
+                meanB += gB[w * GC + lane];
+            }
         }
         meanA /= (double)nA;
         meanB /= (double)nB;
@@ -229,14 +231,13 @@ __device__ __noinline__ int geweke_converged(double *gw, int CTm, int nwarps, in
                 qb = fma(d, d, qb);
             }
         }
-        gA[warp * DG_GW_COLS + lane] = qa;
-        gB[warp * DG_GW_COLS + lane] = qb;
+        if (lane < GC) { gA[warp * GC + lane] = qa; gB[warp * GC + lane] = qb; }
         __syncthreads();
         if (warp == 0 && act) {
             double va = 0.0, vb = 0.0;
             for (int w = 0; w < nwarps; ++w) {
-                va += gA[w * DG_GW_COLS + lane];
-                vb += gB[w * DG_GW_COLS + lane];
+                va += gA[w * GC + lane];
+                vb += gB[w * GC + lane];
             }
             va /= (double)nA;
             vb /= (double)nB;
@@ -255,31 +256,38 @@ __device__ __noinline__ int geweke_converged(double *gw, int CTm, int nwarps, in
 // cannot hide instruction-fetch latency).
 __device__ __noinline__ double dg_log(double x) { return log(x); }
 
-// Fill stream ring entries for steps [s0, s1): increments delta[c,t] and log(u).
-// Device stream: Philox normals z (Box-Muller, both outputs of a pair used), then
-// delta = sqrt(jump_scale[c]) * (z[c,:] @ A_K).  Host stream: delta and u come from the
-// uploaded chunk.  Called by `nprod` threads (index `pt`) which must ALL call it: they
-// synchronise on __syncthreads (all_threads) or on the likelihood-warp barrier.
+// Fill stream ring entries for steps [s0, s1).  A ring row holds CT+2 doubles: the proposal
+// increments delta[c,t] (c < C-1), log(u) at [CT] and the proposal log-density Q at [CT+1].
+//   device stream: Philox normals z (Box-Muller, both outputs used), then
+//                  delta = sqrt(jump_scale[c]) * (z[c,:] @ A_K)
+//   host stream:   delta and u come from the uploaded chunk
+//   Q = sum_c ( jump_const[c] - (d_c K^-1 d_c) / (2 jump_scale[c]) ),  d = Y_now - Y_try = -delta
+//       (model_GP.py:330-331: Q_now and Q_try are the same number; it only enters the MH
+//       exponent as ((P_try + Q) - P_now) - Q, so it is formed here, off the serial path)
+// Called by `nprod` threads (index `pt`) which must ALL call it: they synchronise on
+// __syncthreads (all_threads) or on the likelihood-warp barrier.
 __device__ __noinline__ void produce_stream(bool dev_stream, int s0, int s1, int pt, int nprod, bool all_threads,
-                                            double *zring, double *dring, int RING, int CT, int CTm, int Tc,
-                                            const double *pfac, const double *sqs, uint64_t seed, int64_t sid,
+                                            double *zring, double *dring, int RING, int C, int Tc,
+                                            const double *pfac, const double *sqs, const double *kinv,
+                                            const double *jcon, const double *ijs, uint64_t seed, int64_t sid,
                                             const double *dblk, const double *ublk, int m_start) {
+    const int CT = C * Tc, CTm = CT - Tc, RL = CT + 2;
     if (dev_stream) {
         const int npair = (CTm + 1) >> 1;
         for (int s = s0; s < s1; ++s) {
-            double *z = zring + (s % RING) * CT;
+            double *z = zring + (s % DG_STREAM_BLOCK) * RL;
             for (int i = pt; i < npair; i += nprod) {
                 double z0, z1;
                 dg_normal_pair(seed, sid, (uint32_t)s, (uint32_t)i, z0, z1);
                 z[2 * i] = z0;
                 if (2 * i + 1 < CTm) z[2 * i + 1] = z1;
             }
-            if (pt == nprod - 1) dring[(s % RING) * CT + CT - 1] = dg_log(dg_uniform(seed, sid, (uint32_t)s));
+            if (pt == nprod - 1) dring[(s % RING) * RL + CT] = dg_log(dg_uniform(seed, sid, (uint32_t)s));
         }
         if (all_threads) __syncthreads(); else bar_lik(nprod);
         for (int s = s0; s < s1; ++s) {
-            const double *z = zring + (s % RING) * CT;
-            double *d = dring + (s % RING) * CT;
+            const double *z = zring + (s % DG_STREAM_BLOCK) * RL;
+            double *d = dring + (s % RING) * RL;
             for (int i = pt; i < CTm; i += nprod) {
                 const int c = i / Tc, t = i - c * Tc;
                 double a = 0.0;
@@ -289,11 +297,31 @@ __device__ __noinline__ void produce_stream(bool dev_stream, int s0, int s1, int
         }
     } else {
         for (int s = s0; s < s1; ++s) {
-            double *d = dring + (s % RING) * CT;
+            double *d = dring + (s % RING) * RL;
             const double *src = dblk + (size_t)(s - m_start) * CTm;
             for (int i = pt; i < CTm; i += nprod) d[i] = src[i];
-            if (pt == nprod - 1) d[CT - 1] = dg_log(ublk[s - m_start]);
+            if (pt == nprod - 1) d[CT] = dg_log(ublk[s - m_start]);
         }
+    }
+    if (all_threads) __syncthreads(); else bar_lik(nprod);
+    // per (step, c): d K^-1 d into the z ring (free now)
+    const int nq = (s1 - s0) * (C - 1);
+    for (int q = pt; q < nq; q += nprod) {
+        const int s = s0 + q / (C - 1), c = q - (s - s0) * (C - 1);
+        const double *d = dring + (s % RING) * RL + c * Tc;
+        double acc = 0.0;
+        for (int t = 0; t < Tc; ++t) {
+            double r = 0.0;
+            for (int j = 0; j < Tc; ++j) r = fma(d[j], kinv[j * Tc + t], r);
+            acc += r * d[t];
+        }
+        zring[(s % DG_STREAM_BLOCK) * RL + c] = jcon[c] - (acc * ijs[c]) / 2.0;
+    }
+    if (all_threads) __syncthreads(); else bar_lik(nprod);
+    for (int s = s0 + pt; s < s1; s += nprod) {
+        double Q = 0.0;
+        for (int c = 0; c < C - 1; ++c) Q += zring[(s % DG_STREAM_BLOCK) * RL + c];
+        dring[(s % RING) * RL + CT + 1] = Q;
     }
 }
 
@@ -321,7 +349,9 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                           int slot, int n_steps, double *smem, int use_tma) {
     constexpr int J = (1 << D) - 1;
     constexpr int JP = J + 1;
-    constexpr int RING = 2 * D;
+    constexpr int SB = DG_STREAM_BLOCK;                   // stream steps produced per batch
+    constexpr int RING = 2 * SB;                          // ring of two batches
+    static_assert(SB >= 2 * D, "a stream batch must cover two rounds");
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     if (ct.state[chain] != 0) return;                    // already finished (block-uniform)
@@ -329,11 +359,11 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     const int g = ct.gene[chain], t0 = ct.t0[chain];
     const int C = KC > 0 ? KC : gt.C[g];
     const int Tc = ct.Tc[chain], T = gt.T;
-    const int CT = C * Tc, CTm = (C - 1) * Tc;
+    const int CT = C * Tc, CTm = (C - 1) * Tc, RL = CT + 2;     // RL: doubles per stream ring row
     const int S = (CT + 31) >> 5, nstate = S << 5, NWL = nwarps - S;
     const SmLayout L = dg_layout(C, Tc, nwarps, D);
     double *ycand = smem + L.ycand, *psic = smem + L.psic, *gs = smem + L.gs, *ex = smem + L.ex;
-    double *pr = smem + L.pr, *qq = smem + L.qq, *ff = smem + L.ff, *zring = smem + L.zring, *dring = smem + L.dring;
+    double *pr = smem + L.pr, *ff = smem + L.ff, *zring = smem + L.zring, *dring = smem + L.dring;
     double *kinv = smem + L.kinv, *pfac = smem + L.pfac, *ijs = smem + L.ijs, *jcon = smem + L.jcon, *sqs = smem + L.sqs;
     double *red = smem + L.red, *bc = smem + L.bc, *gw = smem + L.gw;
     int *redi = reinterpret_cast<int *>(smem + L.redi);
@@ -455,9 +485,16 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     long long page_cur = -1;                              // thread 0: page of the last row written
     const double *dblk = dev_stream ? nullptr : sa.delta + sa.delta_off[slot];
     const double *ublk = dev_stream ? nullptr : sa.u + sa.u_off[slot];
-    // stream ring: entries for steps [m, m + RING) (clipped to the chunk)
-    produce_stream(dev_stream, m, min(m + RING, m_end), tid, nthreads, true, zring, dring, RING, CT, CTm, Tc, pfac, sqs,
-                   sa.seed, sid, dblk, ublk, m_start);
+    // stream ring: two batches of SB steps; a new batch is produced (by the likelihood warps,
+    // with all their lanes busy) whenever the chain is within one batch of the end of the ring
+    int produced = m;                                     // ring holds steps [.., produced)
+    for (int b = 0; b < 2 && produced < m_end; ++b) {
+        const int upto = min(produced + SB, m_end);
+        produce_stream(dev_stream, produced, upto, tid, nthreads, true, zring, dring, RING, C, Tc, pfac, sqs, kinv,
+                       jcon, ijs, sa.seed, sid, dblk, ublk, m_start);
+        produced = upto;
+        __syncthreads();
+    }
     __syncthreads();
 #ifdef DG_PROFILE
     long long dg_prof[10];
@@ -487,7 +524,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                     for (int d = 0; d < D; ++d) {
                         int sl = rbase + d;
                         if (sl >= RING) sl -= RING;
-                        dl[d] = d < nd_max ? dring[sl * CT + si] : 0.0;
+                        dl[d] = d < nd_max ? dring[sl * RL + si] : 0.0;
                     }
                     // node j (heap order): state before it proposes = Y_now moved through its accepted
                     // ancestors; Y_try = delta + that state (:329, numpy adds the mean last)
@@ -558,7 +595,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
 #pragma unroll
                 for (int j = 0; j < J; ++j) psic[j * CT + si] = ej[j] / dg_np_sum(ex + j * CT + stt, C, Tc);   // (:335)
             }
-            // GP prior (:332) and proposal density (:330-331): x K^-1 x as (x K^-1)[t] * x[t]
+            // GP prior (:332): x K^-1 x as sum_t (x K^-1)[t] * x[t]
             if (s_free) {
                 double r[J];
 #pragma unroll
@@ -569,44 +606,21 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                     for (int j = 0; j < J; ++j) r[j] = fma(ycand[j * CT + sc * Tc + t2], kv, r[j]);
                 }
 #pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    pr[j * CT + si] = r[j] * yj[j];
-                    qq[j * CT + si] = bj[j] - yj[j];                         // d = Y_now - Y_try
-                }
-            }
-            bar_state(nstate);
-            double qpart[J];
-            if (s_free) {
-#pragma unroll
-                for (int j = 0; j < J; ++j) qpart[j] = 0.0;
-                for (int t2 = 0; t2 < Tc; ++t2) {
-                    const double kv = kinv_col[t2 * Tc];
-#pragma unroll
-                    for (int j = 0; j < J; ++j) qpart[j] = fma(qq[j * CT + sc * Tc + t2], kv, qpart[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < J; ++j) qpart[j] *= (bj[j] - yj[j]);
-            }
-            bar_state(nstate);                                               // everyone has read qq
-            if (s_free) {
-#pragma unroll
-                for (int j = 0; j < J; ++j) qq[j * CT + si] = qpart[j];
+                for (int j = 0; j < J; ++j) pr[j * CT + si] = r[j] * yj[j];
             }
             bar_state(nstate);
             for (int q = tid; q < J * (C - 1); q += nstate) {                // (node, c): sums over t
                 const int jn = q / (C - 1), c = q - jn * (C - 1);
-                const double *prc = pr + jn * CT + c * Tc, *qc = qq + jn * CT + c * Tc;
-                double a = 0.0, b = 0.0;
-                for (int t = 0; t < Tc; ++t) { a += prc[t]; b += qc[t]; }
-                gs[jn * CT + c] = prior_const - a / 2.0;                     // gs / ex are free after B1
-                ex[jn * CT + c] = jcon[c] - (b * ijs[c]) / 2.0;
+                const double *prc = pr + jn * CT + c * Tc;
+                double a = 0.0;
+                for (int t = 0; t < Tc; ++t) a += prc[t];
+                gs[jn * CT + c] = prior_const - a / 2.0;                     // gs is free after B1
             }
             bar_state(nstate);
             for (int q = tid; q < J; q += nstate) {
-                double prior = 0.0, Q = 0.0;                                 // c ascending (:312-332)
-                for (int c = 0; c < C - 1; ++c) { prior += gs[q * CT + c]; Q += ex[q * CT + c]; }
+                double prior = 0.0;                                          // c ascending (:312-332)
+                for (int c = 0; c < C - 1; ++c) prior += gs[q * CT + c];
                 bc[16 + q] = prior;
-                bc[16 + J + q] = init ? 0.0 : Q;
             }
         }
         DG_TICK(1);
@@ -636,8 +650,14 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                         }
                         bad |= __shfl_xor_sync(0xffffffffu, bad, off);
                     }
+                    // lane j takes the logarithm of candidate j (one log latency for all of them)
+                    double mine = mm[0];
+                    int eme = ee[0];
 #pragma unroll
-                    for (int j = 0; j < J; ++j) lik[j] = fma((double)ee[j], 0.693147180559945309417232121458, dg_log(mm[j]));
+                    for (int j = 1; j < J; ++j) if (lane == j) { mine = mm[j]; eme = ee[j]; }
+                    const double lk = fma((double)eme, 0.693147180559945309417232121458, log(mine));
+#pragma unroll
+                    for (int j = 0; j < J; ++j) lik[j] = __shfl_sync(0xffffffffu, lk, j);
                 } else {
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
@@ -670,14 +690,14 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                             // tested in the log domain with log(u) taken off the critical path
                             int node = 0, cur = -1;
                             for (int d = 0; d < nd_ok; ++d) {
-                                double likn = lik[0], priorn = bc[16 + node], Q = bc[16 + J + node];
+                                double likn = lik[0], priorn = bc[16 + node];
 #pragma unroll
                                 for (int j = 1; j < J; ++j) if (j == node) likn = lik[j];
                                 const double P_try = priorn + likn;
-                                const double a = ((P_try + Q) - P_now) - Q;
                                 int sl = rbase + d;
                                 if (sl >= RING) sl -= RING;
-                                const double lu = dring[sl * CT + CT - 1];
+                                const double lu = dring[sl * RL + CT], Q = dring[sl * RL + CT + 1];
+                                const double a = ((P_try + Q) - P_now) - Q;
                                 const bool acc = (a >= 0.0) || (lu < a);     // NaN a: both false
                                 if (!isfinite(P_try)) flags |= 1;
                                 if (acc) { ++cnt; P_now = P_try; L_now = likn; cur = node; }
@@ -722,11 +742,12 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                 }
             }
             bar_state(nstate);                                               // candidates may be overwritten now
-        } else if (!init && nd > 0) {
-            // ring entries of the steps just consumed are free: refill them RING steps ahead
-            produce_stream(dev_stream, min(m + RING, m_end), min(m + nd + RING, m_end), tid - nstate, nthreads - nstate,
-                           false, zring, dring, RING, CT, CTm, Tc, pfac, sqs, sa.seed, sid, dblk, ublk, m_start);
+        } else if (!init && produced < m_end && produced - (m + nd) <= SB) {
+            // the batch behind the chain is consumed: overwrite it with the next SB steps
+            produce_stream(dev_stream, produced, min(produced + SB, m_end), tid - nstate, nthreads - nstate,
+                           false, zring, dring, RING, C, Tc, pfac, sqs, kinv, jcon, ijs, sa.seed, sid, dblk, ublk, m_start);
         }
+        if (!init && produced < m_end && produced - (m + nd) <= SB) produced = min(produced + SB, m_end);
         if (init) { init = false; continue; }
         m += nd;
         rbase += nd;

@@ -16,6 +16,7 @@
 #define DG_MAXTHREADS 1024
 #define DG_MAXWARPS 32
 #define DG_GW_COLS 32         // Geweke column tile
+#define DG_STREAM_BLOCK 8      // random-stream steps produced per batch (ring = 2 batches)
 
 // ---------------------------------------------------------------------------------------
 // tables (device pointers, passed by value to the kernels)
@@ -85,9 +86,9 @@ struct TraceView {
 // ---------------------------------------------------------------------------------------
 struct SmLayout {
     // offsets in doubles from the start of dynamic shared memory
-    int ycand, psic, gs, ex, pr, qq;                           // J*CT each (J = 2^D - 1 candidates)
+    int ycand, psic, gs, ex, pr;                               // J*CT each (J = 2^D - 1 candidates)
     int ff;                                                    // CT*(J+1): f of all candidates, [t][k][j]
-    int zring, dring;                                          // 2*D*CT each: stream ring (z, delta + log u)
+    int zring, dring;                                          // stream: one batch of z / scratch; ring of delta, log u, Q
     int kinv, pfac;                                            // Tc*Tc each
     int ijs, jcon, sqs;                                        // C each
     int red, redi, redb, bc, gw, rel, seg, mbar;               // scratch
@@ -97,20 +98,20 @@ struct SmLayout {
 
 __host__ __device__ inline SmLayout dg_layout(int C, int Tc, int nwarps, int D) {
     SmLayout L;
-    const int J = (1 << D) - 1, JP = J + 1, RING = 2 * D;
+    const int J = (1 << D) - 1, JP = J + 1, RING = 2 * DG_STREAM_BLOCK;
     int CT = C * Tc, TT = Tc * Tc, o = 0;
     L.ycand = o; o += J * CT;  L.psic = o; o += J * CT;  L.gs = o; o += J * CT;  L.ex = o; o += J * CT;
-    L.pr = o; o += J * CT;     L.qq = o; o += J * CT;
+    L.pr = o; o += J * CT;
     o = (o + 1) & ~1;
     L.ff = o; o += CT * JP;                    // 16-byte aligned rows of JP doubles
-    L.zring = o; o += RING * CT;  L.dring = o; o += RING * CT;
+    L.zring = o; o += DG_STREAM_BLOCK * (CT + 2);  L.dring = o; o += RING * (CT + 2);
     L.kinv = o; o += TT;  L.pfac = o; o += TT;
     L.ijs = o; o += C;    L.jcon = o; o += C;  L.sqs = o; o += C;
     L.red = o; o += J * DG_MAXWARPS;
     L.redi = o; o += J * DG_MAXWARPS / 2 + 1;  // ints
     L.redb = o; o += DG_MAXWARPS / 2;          // unsigned
     L.bc = o; o += 64;
-    L.gw = o; o += 2 * nwarps * DG_GW_COLS;
+    { const int ctm = CT - Tc; L.gw = o; o += 2 * nwarps * (ctm < DG_GW_COLS ? (ctm > 0 ? ctm : 1) : DG_GW_COLS); }
     L.rel = o; o += Tc + 2;                    // ints: rel roff[Tc+1], ncnt[Tc]
     L.seg = o; o += (DG_MAXT + 2) / 2 + 1;     // ints: first 32-pair item of each time point
     L.mbar = o; o += 2;
