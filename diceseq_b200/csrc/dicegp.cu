@@ -352,6 +352,9 @@ struct dicegp_ctx {
     DevBuf<int64_t> ddoff;
     DevBuf<double> ddelta, du, dvar;
     DevBuf<int> dqueue;
+    DevBuf<double> smean, sci, slik;       // posterior summary scratch
+    DevBuf<int64_t> soff;
+    DevBuf<int32_t> sids;
     DevBuf<unsigned long long> dprof;
     double last_ms = 0.0;
     int64_t last_launches = 0, last_evals = 0, last_steps = 0;
@@ -473,18 +476,21 @@ chain_kernel_t chain_kernel_for(int kind, bool w_in_smem) {
 // Common driver: advance `ids` (host order) by n_steps with stream args `sa`.
 // The kernel's slot is the position in the per-group id list, so the per-slot host-stream
 // offsets are permuted alongside.
+// latency_mode: few chains are left (the stragglers of a batch); give each as many likelihood
+// warps as fit instead of packing many chains per SM.
 int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, StreamArgs sa,
-               const std::vector<int64_t> *delta_off, bool persistent) {
+               const std::vector<int64_t> *delta_off, bool persistent, bool latency_mode = false) {
     LaunchClass cls[kTiers];
     launch_classes(c, cls);
+    if (latency_mode) {
+        for (int i = 0; i < 4; ++i) { cls[i].threads = DG_LB_THREADS; cls[i].blocks_per_sm = 1; }
+    }
     std::vector<int32_t> by_group[kGroups];
     std::vector<int32_t> slot_src[kGroups];
     for (size_t i = 0; i < ids.size(); ++i) {
         const dicegp_chain_desc &d = c->hdesc[ids[i]];
         const int C = c->hC[d.gene];
         int tier = pick_tier(c, cls, ids[i]);
-        if (tier == 4 && cls[4].threads < min_threads(C, d.Tc))
-            return c->fail(DICEGP_ERR_LIMIT, "chain has too many latent values for the streaming tier");
         const int k = tier * kKinds + kind_of(C);
         by_group[k].push_back(ids[i]);
         slot_src[k].push_back((int32_t)i);
@@ -547,16 +553,45 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             const int k = tier * kKinds + kind;
             const int n_ids = (int)by_group[k].size();
             if (n_ids == 0) continue;
+            // launch shape: resident tiers use the tier's block size; the streaming tier plans
+            // (likelihood warps per chain, chains per SM) from the group's shapes so that as many
+            // streaming warps as possible are resident: threads*k <= DG_LB_THREADS (registers),
+            // smem*k <= what an SM offers, at most 4 chains per SM
+            int threads = cls[tier].threads, bps = cls[tier].blocks_per_sm;
+            int maxC = 1, maxTc = 1, maxS = 1;
+            for (int32_t id : by_group[k]) {
+                const dicegp_chain_desc &d = c->hdesc[id];
+                maxC = std::max(maxC, c->hC[d.gene]);
+                maxTc = std::max(maxTc, d.Tc);
+                maxS = std::max(maxS, (c->hC[d.gene] * d.Tc + 31) / 32);
+            }
+            if (tier == 4 && !getenv("DICEGP_TIER_THREADS")) {
+                int best_score = -1;
+                for (int kk = 1; kk <= (latency_mode ? 1 : 4); ++kk) {
+                    for (int nwl = 2; nwl <= 14; ++nwl) {
+                        const int thr = 32 * (maxS + nwl);
+                        if (thr * kk > DG_LB_THREADS) continue;
+                        size_t need = fixed_smem_bytes(maxC, maxTc, thr) + 1024;
+                        if (kind != 0) need += (size_t)nwl * dg::kStages * maxC * 512;
+                        if (need * kk > 233472) continue;
+                        // at least 8 streaming warps per SM, then as many chains as possible (their serial
+                        // phases overlap), then more warps
+                        const int score = latency_mode ? nwl : std::min(kk * nwl, 8) * 100 + kk * 10 + nwl;
+                        if (score > best_score) { best_score = score; threads = thr; bps = kk; }
+                    }
+                }
+                if (best_score < 0) return c->fail(DICEGP_ERR_LIMIT, "chain has too many latent values for the streaming tier");
+            }
             // dynamic shared memory of this launch: the largest need among its chains
             size_t smem = 0;
             for (int32_t id : by_group[k]) {
                 const dicegp_chain_desc &d = c->hdesc[id];
-                size_t need = fixed_smem_bytes(c->hC[d.gene], d.Tc, cls[tier].threads);
+                size_t need = fixed_smem_bytes(c->hC[d.gene], d.Tc, threads);
                 if (cls[tier].w_in_smem) need += (size_t)chain_wbytes(c, id);
                 else if (kind != 0) {
                     // per likelihood warp: kStages x C x 32 lanes x 16 bytes of cp.async staging
                     const int C = c->hC[d.gene];
-                    const int nwl = cls[tier].threads / 32 - (C * d.Tc + 31) / 32;
+                    const int nwl = threads / 32 - (C * d.Tc + 31) / 32;
                     need += (size_t)nwl * dg::kStages * C * 512;
                 }
                 smem = std::max(smem, need);
@@ -574,13 +609,13 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             int grid = n_ids;
             int *queue = nullptr;
             if (persistent) {
-                grid = std::min(n_ids, c->sm_count * cls[tier].blocks_per_sm);
+                grid = std::min(n_ids, c->sm_count * bps);
                 queue = c->dqueue.p + k;
             }
             chain_kernel_t kern = chain_kernel_for(kind, cls[tier].w_in_smem);
             DG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(c->smem_optin - c->static_smem)));
-            kern<<<grid, cls[tier].threads, smem, st>>>(gt, ct, sak, c->dids.p + base[k], n_ids, n_steps, c->use_tma, queue);
+            kern<<<grid, threads, smem, st>>>(gt, ct, sak, c->dids.p + base[k], n_ids, n_steps, c->use_tma, queue);
             {
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return c->cuda_fail(e, "chain kernel launch");
@@ -703,6 +738,7 @@ int dicegp_destroy(dicegp_ctx *c) {
     c->cprior.release(); c->cpool.release(); c->ctrace.release(); c->cst.release();
     c->dids.release(); c->ddoff.release(); c->ddelta.release(); c->du.release(); c->dvar.release();
     c->dqueue.release();
+    c->smean.release(); c->sci.release(); c->slik.release(); c->soff.release(); c->sids.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -985,7 +1021,31 @@ int dicegp_run_device_stream(dicegp_ctx *c, uint64_t seed, const int64_t *stream
     memset(&sa, 0, sizeof sa);
     sa.mode = 1;
     sa.seed = seed;
-    return run_chains(c, ids, max_M, sa, nullptr, true);
+    // Pass 1 (throughput shapes): every chain, capped at kStragglerSteps.  Pass 2 (latency
+    // shapes): the few chains still running -- they would otherwise crawl along with the two or
+    // three likelihood warps of the throughput shape while the rest of the GPU idles.  The
+    // stream is counter based, so a resumed chain continues bit-identically.
+    const int kStragglerSteps = 4096;
+    const char *env_cap = getenv("DICEGP_STRAGGLER_STEPS");
+    const int cap = env_cap ? atoi(env_cap) : kStragglerSteps;
+    if (cap <= 0 || max_M <= cap) return run_chains(c, ids, max_M, sa, nullptr, true);
+    int rc = run_chains(c, ids, cap, sa, nullptr, true);
+    if (rc != DICEGP_OK) return rc;
+    const double ms1 = c->last_ms;
+    const int64_t l1 = c->last_launches, e1 = c->last_evals, s1 = c->last_steps;
+    std::vector<int32_t> st(c->n_chains);
+    DG_CUDA(c, cudaMemcpy(st.data(), c->cstate.p, c->n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> rest;
+    for (int i = 0; i < c->n_chains; ++i) if (st[i] == DICEGP_CHAIN_RUNNING) rest.push_back(i);
+    if (!rest.empty()) {
+        rc = run_chains(c, rest, max_M, sa, nullptr, true, true);
+        if (rc != DICEGP_OK) return rc;
+        if (getenv("DICEGP_VERBOSE"))
+            fprintf(stderr, "[dicegp] pass1 %.1f ms (%lld steps, %d chains)  pass2 %.1f ms (%lld steps, %zu chains)\n", ms1,
+                    (long long)s1, c->n_chains, c->last_ms, (long long)c->last_steps, rest.size());
+        c->last_ms += ms1; c->last_launches += l1; c->last_evals += e1; c->last_steps += s1;
+    }
+    return DICEGP_OK;
 }
 
 int dicegp_chain_status(dicegp_ctx *c, int32_t n, const int32_t *chain_ids, int32_t *m_ret, int32_t *n_rows,
@@ -1075,14 +1135,12 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
     std::vector<int32_t> ids_sorted(n);
     std::vector<int64_t> off_sorted(n);
     for (int i = 0; i < n; ++i) { ids_sorted[i] = chain_ids[order[i]]; off_sorted[i] = out_off[order[i]]; }
-    DevBuf<double> dmean, dci, dlik;
-    DevBuf<int64_t> doff;
-    DevBuf<int32_t> dids;
+    DevBuf<double> &dmean = c->smean, &dci = c->sci, &dlik = c->slik;
+    DevBuf<int64_t> &doff = c->soff;
+    DevBuf<int32_t> &dids = c->sids;
     if (dmean.resize(total) != cudaSuccess || dci.resize(2 * total) != cudaSuccess || dlik.resize(n) != cudaSuccess ||
-        doff.resize(n) != cudaSuccess || dids.resize(n) != cudaSuccess) {
-        dmean.release(); dci.release(); dlik.release(); doff.release(); dids.release();
+        doff.resize(n) != cudaSuccess || dids.resize(n) != cudaSuccess)
         return c->fail(DICEGP_ERR_NOMEM, "posterior_summary: device allocation failed");
-    }
     int rc = DICEGP_OK;
     cudaError_t e;
     std::vector<double> lik_sorted(n);
@@ -1110,7 +1168,6 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
         for (int i = 0; i < n; ++i) lik_marg[order[i]] = lik_sorted[i];
         c->d2h_bytes += (3 * total + n) * (int64_t)sizeof(double);
     }
-    dmean.release(); dci.release(); dlik.release(); doff.release(); dids.release();
     return rc;
 }
 
