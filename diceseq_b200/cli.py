@@ -1,0 +1,193 @@
+"""`diceseq` command line, drop-in for `diceseq/diceseq.py`.
+
+Same flags, same `.dice` / `.sample.gz` formats, same transcript order (the reference sorts
+its output back into annotation order, `run_utils.py:39-46`).  The work is restructured into
+three stages: (1) host: read->isoform matrices of every gene (optionally over a process
+pool, `-p`), (2) GPU: all multi-isoform genes sampled in batches by `BatchSampler`
+(pre-runs, jump variance, joint chains, summaries on the device), (3) host: formatting.
+
+Differences, all deliberate: single-isoform genes get psi = 1 rows instead of crashing the
+worker; `.sample.gz` is written in text mode (Appendix B #11);
+`--bias` modes other than `unif` and `--thetas x learn` are refused (need a FASTA / are
+not offloaded); extra flags `--device`, `--seed`, `--batch`.
+
+    python -m diceseq_b200.cli -a anno.gtf -s t1.bam---t2.bam---t3.bam -t 1.5,2.5,5 -o out/joint --add_premRNA
+"""
+from __future__ import annotations
+
+import gzip
+import os
+import sys
+import time
+from optparse import OptionGroup, OptionParser
+
+import numpy as np
+
+from .annotation import loadgene
+from .bam import load_samfile
+from .run_utils import format_dice_lines, format_sample_lines, gene_inputs, single_isoform_result
+
+
+def build_parser():
+    parser = OptionParser()
+    parser.add_option("--anno_file", "-a", dest="anno_file", default=None,
+                      help="Annotation file for genes and transcripts in GTF or GFF3")
+    parser.add_option("--sam_list", "-s", dest="sam_list", default=None,
+                      help=("Sorted and indexed bam/sam files, use ',' for replicates "
+                            "and '---' for time points, e.g., T1_rep1.bam,T1_rep2.bam---T2.bam"))
+    parser.add_option("--time_seq", "-t", dest="time_seq", default=None,
+                      help="The time for the input samples [Default: 0,1,2,...]")
+    parser.add_option("--out_file", "-o", dest="out_file", default="output",
+                      help="Prefix of the output files with full path")
+    group = OptionGroup(parser, "Optional arguments")
+    group.add_option("--nproc", "-p", type="int", dest="nproc", default="4",
+                     help="Number of subprocesses for building the read matrices [default: %default]")
+    group.add_option("--add_premRNA", action="store_true", dest="add_premRNA", default=False,
+                     help="Add the pre-mRNA as a transcript")
+    group.add_option("--fLen", type="float", nargs=2, dest="frag_leng", default=[None, None],
+                     help="Two arguments for fragment length: mean and standard diveation, default: auto-detected")
+    group.add_option("--bias", nargs=3, dest="bias_args", default=["unif", "None", "None"],
+                     help="Three argments for bias correction: BIAS_MODE,REF_FILE,BIAS_FILE(s) [default: unif None None]")
+    group.add_option("--thetas", nargs=2, dest="thetas", default=[3, "None"],
+                     help="Two arguments for hyperparameters in GP model: theta1,theta2. default: [3 None], "
+                          "where theta2 covers 1/3 duration.")
+    group.add_option("--mcmc", type="int", nargs=4, dest="mcmc_run", default=[0, 20000, 1000, 100],
+                     help="Four arguments for in MCMC iterations: save_sample,max_run,min_run,gap_run. "
+                          "[default: 0 20000 1000 100]")
+    group.add_option("--device", type="int", dest="device", default=0, help="GPU index [default: %default]")
+    group.add_option("--seed", type="int", dest="seed", default=0, help="seed of the device random stream")
+    group.add_option("--batch", type="int", dest="batch", default=20000, help="genes per GPU batch")
+    parser.add_option_group(group)
+    return parser
+
+
+def _inputs_worker(args):
+    gene, sam_list, FLmean, FLstd = args
+    return gene_inputs(gene, sam_list, FLmean, FLstd)
+
+
+def main(argv=None):
+    parser = build_parser()
+    argv = sys.argv[1:] if argv is None else argv
+    options, _args = parser.parse_args(argv)
+    if len(argv) == 0:
+        print("Welcome to diceseq!\n")
+        print("use -h or --help for help on argument.")
+        sys.exit(1)
+    if options.anno_file is None:
+        print("[DICEseq] Error: need --anno_file for annotation.")
+        sys.exit(1)
+    sys.stdout.write("\r[DICEseq] loading annotation file...")
+    sys.stdout.flush()
+    genes = loadgene(options.anno_file)
+    sys.stdout.write("\r[DICEseq] loading annotation file... Done.\n")
+    if options.sam_list is None:
+        print("[DICEseq] Error: need --sam_list for aliged & indexed reads.")
+        sys.exit(1)
+    sam_list = [tp.split(",") for tp in options.sam_list.split("---")]
+    TOTAL_READ = []
+    for files in sam_list:
+        cnt = 0.0
+        for ss in files:
+            if not os.path.isfile(ss):
+                print("Error: No such file\n    -- %s" % ss)
+                sys.exit(1)
+            cnt += load_samfile(ss).mapped_total()                 # pysam.idxstats column 3 (diceseq.py:141-147)
+        TOTAL_READ.append(cnt)
+
+    FLmean, FLstd = options.frag_leng
+    sample_num, Mmax, Mmin, Mgap = options.mcmc_run
+    X = np.arange(len(sam_list)) if options.time_seq is None else np.array(options.time_seq.split(","), "float")
+    theta1, theta2 = options.thetas
+    theta1 = float(theta1)
+    if theta2 is None or theta2 in ("None", "Auto", "auto"):
+        theta2 = ((max(X) - min(X) + 0.1) / 3.0) ** 2                # diceseq.py:169
+    elif theta2 == "learn":
+        print("[DICEseq] Error: --thetas x learn (sampling theta2) is not supported by the GPU sampler.")
+        sys.exit(1)
+    else:
+        theta2 = max(0.00001, float(theta2))
+    if options.bias_args[0] != "unif":
+        print("[DICEseq] Error: only --bias unif is supported (bias modes need a reference FASTA and bias file).")
+        sys.exit(1)
+
+    if options.add_premRNA:
+        for g in genes:
+            g.add_premRNA()
+    T = len(X)
+    start_time = time.time()
+    print("[DICEseq] running diceseq for %d genes on GPU %d (matrices on %d cores)..." % (
+        len(genes), options.device, options.nproc))
+
+    # ---- stage 1: host matrices -------------------------------------------------------------
+    jobs = [(g, sam_list, FLmean, FLstd) for g in genes]
+    if options.nproc <= 1 or len(genes) < 4:
+        inputs = [_inputs_worker(j) for j in jobs]
+    else:
+        import multiprocessing
+        with multiprocessing.get_context("fork").Pool(options.nproc) as pool:
+            inputs = pool.map(_inputs_worker, jobs, chunksize=max(1, len(jobs) // (8 * options.nproc)))
+
+    # ---- stage 2: GPU sampling of the multi-isoform genes -----------------------------------
+    from .batch import BatchSampler
+    from .packer import clean_inputs, pack_genes
+    multi = [i for i, g in enumerate(genes) if g.tranNum > 1]
+    results = {}
+    samples = {}
+    sampler = BatchSampler(options.device) if multi else None
+    for b0 in range(0, len(multi), options.batch):
+        idx = multi[b0:b0 + options.batch]
+        packed_in = []
+        for i in idx:
+            R_all, len_all, prob_all, _count = inputs[i]
+            clean_inputs(R_all, len_all, prob_all)                   # model_GP.py:250-264
+            packed_in.append(([R * P for R, P in zip(R_all, prob_all)], len_all))
+        res = sampler.run(pack_genes(packed_in), X=X, theta1=theta1, theta2=theta2, M=Mmax, initial=Mmin,
+                          gap=Mgap, seed=options.seed, gene_ids=np.array(idx))
+        for k, i in enumerate(idx):
+            results[i] = res[k]
+            if sample_num > 0:
+                m = res[k].m
+                n_keep = min(int(0.5 * m), sample_num)
+                if n_keep > 0:
+                    _psi, Y, _pro, _lik = sampler.ctx.download_trace(k, n_keep, first_row=int(m / 2))
+                    samples[i] = Y
+                else:
+                    samples[i] = np.zeros((0, genes[i].tranNum, T))
+        sys.stdout.write("\r[DICEseq] %d / %d genes sampled in %.1f sec." % (min(b0 + options.batch, len(multi)),
+                                                                             len(multi), time.time() - start_time))
+        sys.stdout.flush()
+    if sampler is not None:
+        sampler.close()
+
+    # ---- stage 3: output, in annotation order -----------------------------------------------
+    out_dir = os.path.dirname(options.out_file)
+    if out_dir and not os.path.isdir(out_dir):
+        os.makedirs(out_dir, exist_ok=True)
+    with open(options.out_file + ".dice", "w") as fid1:
+        headline = "tran_id\tgene_id\tlogLik\ttransLen"
+        for i in range(T):
+            _t = str(X[i])
+            headline += "\tFPKM_T%s\tratio_T%s\tratio_lo_T%s\tratio_hi_T%s" % (_t, _t, _t, _t)
+        fid1.write(headline + "\n")
+        fid2 = None
+        if sample_num > 0:
+            fid2 = gzip.open(options.out_file + ".sample.gz", "wt")
+            fid2.write("# MCMC samples for latent Y\n# @gene|transcripts|theta2\n# y_c1t1,y_c2t1;y_c1t2,y_c2t2;...\n")
+        for i, g in enumerate(genes):
+            count = inputs[i][3]
+            if g.tranNum > 1:
+                r = results[i]
+                psi_mean, psi_95, lik_marg = r.psi_mean, r.psi_95, r.lik_marg
+            else:
+                psi_mean, psi_95, lik_marg = single_isoform_result(T)
+            fid1.write(format_dice_lines(g, X, count, TOTAL_READ, psi_mean, psi_95, lik_marg))
+            if fid2 is not None and g.tranNum > 1:
+                fid2.write(format_sample_lines(g, theta2, samples[i], g.tranNum))
+        if fid2 is not None:
+            fid2.close()
+    print("\n[DICEseq] done: %s.dice (%d genes, %.1f sec)." % (options.out_file, len(genes), time.time() - start_time))
+
+
+if __name__ == "__main__":
+    main()
