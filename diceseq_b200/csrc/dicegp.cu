@@ -38,17 +38,32 @@ dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__res
                     int n_steps, int use_tma, int *queue) {
     extern __shared__ __align__(128) double dg_smem[];
     __shared__ int next_slot;
-    int slot = blockIdx.x;
+    // cluster launch (large genes): the blocks of a cluster work on the same chain
+    const int cs = (int)dg::cluster_size(), crank = (int)dg::cluster_rank();
+    int slot = blockIdx.x / cs;
     while (true) {
         if (queue != nullptr) {
-            if (threadIdx.x == 0) next_slot = atomicAdd(queue, 1);
-            __syncthreads();
-            slot = next_slot;
-            __syncthreads();
+            if (cs == 1) {
+                if (threadIdx.x == 0) next_slot = atomicAdd(queue, 1);
+                __syncthreads();
+                slot = next_slot;
+                __syncthreads();
+            } else {
+                if (crank == 0 && threadIdx.x == 0) {
+                    const int sl = atomicAdd(queue, 1);
+                    for (int r = 0; r < cs; ++r) dg::st_cluster(&next_slot, r, sl);
+                }
+                dg::cluster_barrier();
+                slot = next_slot;
+                dg::cluster_barrier();
+            }
         }
         if (slot >= n_ids) break;
-        dg::run_chain<KC, WMODE, DG_SPEC_DEPTH>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma);
-        __syncthreads();
+        // every block of the cluster reads the chain state BEFORE the lead block may change it
+        const bool running = ct.state[ids[slot]] == 0;
+        if (cs > 1) dg::cluster_barrier();
+        if (running) dg::run_chain<KC, WMODE, DG_SPEC_DEPTH>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma, cs, crank);
+        if (cs == 1) __syncthreads(); else dg::cluster_barrier();
         if (queue == nullptr) break;
     }
 }
@@ -319,7 +334,7 @@ struct dicegp_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     cudaStream_t class_stream[16] = {};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[40] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[64] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     int64_t total_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     int use_tma = 1;
 
@@ -401,7 +416,7 @@ ChainTab make_chain_tab(dicegp_ctx *c) {
 // Residency tiers: W resident in shared memory at 8/4/2/1 blocks per SM, then the tier
 // that streams W from L2/HBM every step.  Each tier is further split by isoform count,
 // because the likelihood loop is compiled per C (weights f[C] in registers).
-constexpr int kTiers = 5;
+constexpr int kTiers = 8;                     // 0-3 resident, 4 streamed, 5-7 streamed over a cluster of 2/4/8 blocks
 constexpr int kKinds = 8;                      // kernel variants by C: generic, 2..8
 constexpr int kGroups = kTiers * kKinds;
 void launch_classes(const dicegp_ctx *c, LaunchClass out[kTiers]) {
@@ -414,6 +429,7 @@ void launch_classes(const dicegp_ctx *c, LaunchClass out[kTiers]) {
         out[i] = {thr[i], lim, bps[i], true};
     }
     out[4] = {256, 0, 2, false};
+    for (int i = 5; i < kTiers; ++i) out[i] = {DG_LB_THREADS, 0, 1, false};
     // development overrides: DICEGP_TIER_THREADS / DICEGP_TIER_BPS = five comma-separated ints
     const char *et = getenv("DICEGP_TIER_THREADS"), *eb = getenv("DICEGP_TIER_BPS");
     if (et) sscanf(et, "%d,%d,%d,%d,%d", &out[0].threads, &out[1].threads, &out[2].threads, &out[3].threads, &out[4].threads);
@@ -425,9 +441,10 @@ void launch_classes(const dicegp_ctx *c, LaunchClass out[kTiers]) {
     }
 }
 
-size_t fixed_smem_bytes(int C, int Tc, int threads) {
-    return (size_t)dg_layout(C, Tc, (threads + 31) / 32, DG_SPEC_DEPTH).total * sizeof(double);
+size_t fixed_smem_bytes(int C, int Tc, int threads, int cs = 1) {
+    return (size_t)dg_layout(C, Tc, (threads + 31) / 32, DG_SPEC_DEPTH, cs).total * sizeof(double);
 }
+inline int tier_cluster(int tier) { return tier < 5 ? 1 : (2 << (tier - 5)); }
 
 int64_t chain_reads(const dicegp_ctx *c, int chain) {
     const dicegp_chain_desc &d = c->hdesc[chain];
@@ -451,11 +468,45 @@ int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain) {
     const dicegp_chain_desc &d = c->hdesc[chain];
     const int C = c->hC[d.gene];
     const int64_t wb = chain_wbytes(c, chain);
+    // large genes: one chain over a cluster of blocks (the reads split over 2/4/8 SMs)
+    static const int64_t wide_min = getenv("DICEGP_WIDE_MIN_BYTES") ? atoll(getenv("DICEGP_WIDE_MIN_BYTES")) : (1ll << 20);
+    if (wb >= 16 * wide_min) return 7;
+    if (wb >= 4 * wide_min) return 6;
+    if (wb >= wide_min) return 5;
     for (int i = 0; i < 4; ++i) {
         if (cls[i].threads < min_threads(C, d.Tc)) continue;
         if (fixed_smem_bytes(C, d.Tc, cls[i].threads) + (size_t)wb <= cls[i].smem_limit) return i;
     }
     return 4;
+}
+
+// Chains that run on a cluster never allocate trace pages on the device (only the lead block
+// writes the trace, and the blocks must stay in lockstep): give them all their pages now.
+int preallocate_trace_pages(dicegp_ctx *c, const std::vector<int32_t> &ids) {
+    unsigned long long head = 0;
+    DG_CUDA(c, cudaMemcpy(&head, c->cpool_head.p, sizeof head, cudaMemcpyDeviceToHost));
+    for (int32_t id : ids) {
+        const dicegp_chain_desc &d = c->hdesc[id];
+        const int64_t rowlen = 2 * (int64_t)c->hC[d.gene] * d.Tc + 2;
+        const int shift = c->hpshift[id];
+        const int n_pages = (d.M + (1 << shift) - 1) >> shift;
+        std::vector<int64_t> tab(n_pages);
+        DG_CUDA(c, cudaMemcpy(tab.data(), c->cptab.p + c->hptab_off[id], n_pages * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        bool changed = false;
+        for (int p = 0; p < n_pages; ++p) {
+            if (tab[p] >= 0) continue;
+            const unsigned long long need = (unsigned long long)rowlen << shift;
+            if (head + need > (unsigned long long)c->pool_cap)
+                return c->fail(DICEGP_ERR_NOMEM, "trace pool too small for the large genes of this batch; raise the trace budget");
+            tab[p] = (int64_t)head;
+            head += need;
+            changed = true;
+        }
+        if (changed)
+            DG_CUDA(c, cudaMemcpy(c->cptab.p + c->hptab_off[id], tab.data(), n_pages * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    DG_CUDA(c, cudaMemcpy(c->cpool_head.p, &head, sizeof head, cudaMemcpyHostToDevice));
+    return DICEGP_OK;
 }
 
 typedef void (*chain_kernel_t)(GeneTab, ChainTab, StreamArgs, const int32_t *, int, int, int, int *);
@@ -546,7 +597,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     int64_t launches = 0;
     int next_stream = 0;
     // big tiers first: the 1-block-per-SM and streaming launches carry most of the work
-    const int tier_order[kTiers] = {4, 3, 2, 1, 0};
+    const int tier_order[kTiers] = {7, 6, 5, 4, 3, 2, 1, 0};
     for (int to = 0; to < kTiers; ++to) {
         for (int kind = 0; kind < kKinds; ++kind) {
             const int tier = tier_order[to];
@@ -565,6 +616,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                 maxTc = std::max(maxTc, d.Tc);
                 maxS = std::max(maxS, (c->hC[d.gene] * d.Tc + 31) / 32);
             }
+            const int cs = tier_cluster(tier);
             if (tier == 4 && !getenv("DICEGP_TIER_THREADS")) {
                 int best_score = -1;
                 for (int kk = 1; kk <= (latency_mode ? 1 : 4); ++kk) {
@@ -582,11 +634,27 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                 }
                 if (best_score < 0) return c->fail(DICEGP_ERR_LIMIT, "chain has too many latent values for the streaming tier");
             }
+            if (tier >= 5) {
+                // cluster tier: as many likelihood warps per block as the staging ring allows
+                int best = -1;
+                for (int nwl = 2; nwl <= 14; ++nwl) {
+                    const int thr = 32 * (maxS + nwl);
+                    if (thr > DG_LB_THREADS) break;
+                    size_t need = fixed_smem_bytes(maxC, maxTc, thr, cs) + 1024;
+                    if (kind != 0) need += (size_t)nwl * dg::kStages * maxC * 512;
+                    if (need > 233472) break;
+                    best = thr;
+                }
+                if (best < 0) return c->fail(DICEGP_ERR_LIMIT, "chain has too many latent values for the cluster tier");
+                threads = best; bps = 1;
+                int rc = preallocate_trace_pages(c, by_group[k]);
+                if (rc != DICEGP_OK) return rc;
+            }
             // dynamic shared memory of this launch: the largest need among its chains
             size_t smem = 0;
             for (int32_t id : by_group[k]) {
                 const dicegp_chain_desc &d = c->hdesc[id];
-                size_t need = fixed_smem_bytes(c->hC[d.gene], d.Tc, threads);
+                size_t need = fixed_smem_bytes(c->hC[d.gene], d.Tc, threads, cs);
                 if (cls[tier].w_in_smem) need += (size_t)chain_wbytes(c, id);
                 else if (kind != 0) {
                     // per likelihood warp: kStages x C x 32 lanes x 16 bytes of cp.async staging
@@ -609,15 +677,24 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             int grid = n_ids;
             int *queue = nullptr;
             if (persistent) {
-                grid = std::min(n_ids, c->sm_count * bps);
+                grid = std::min(n_ids, c->sm_count * bps / cs);
                 queue = c->dqueue.p + k;
             }
+            grid *= cs;
             chain_kernel_t kern = chain_kernel_for(kind, cls[tier].w_in_smem);
             DG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(c->smem_optin - c->static_smem)));
-            kern<<<grid, threads, smem, st>>>(gt, ct, sak, c->dids.p + base[k], n_ids, n_steps, c->use_tma, queue);
             {
-                cudaError_t e = cudaGetLastError();
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof cfg);
+                cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                const int32_t *ids_arg = c->dids.p + base[k];
+                cudaError_t e = cudaLaunchKernelEx(&cfg, kern, gt, ct, sak, ids_arg, n_ids, n_steps, c->use_tma, queue);
+                if (e == cudaSuccess) e = cudaGetLastError();
                 if (e != cudaSuccess) return c->cuda_fail(e, "chain kernel launch");
             }
             ++launches;
@@ -711,7 +788,7 @@ int dicegp_create(int device, dicegp_ctx **out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) goto fail;
     for (int k = 0; k < kStreams; ++k)
         if (cudaStreamCreateWithFlags(&c->class_stream[k], cudaStreamNonBlocking) != cudaSuccess) goto fail;
-    for (int k = 0; k < 40; ++k)
+    for (int k = 0; k < 64; ++k)
         if (cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) goto fail;
     if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) goto fail;
     if (cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess) goto fail;
@@ -744,7 +821,7 @@ int dicegp_destroy(dicegp_ctx *c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
-    for (int k = 0; k < 40; ++k)
+    for (int k = 0; k < 64; ++k)
         if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
     for (int k = 0; k < kStreams; ++k)
         if (c->class_stream[k]) cudaStreamDestroy(c->class_stream[k]);

@@ -29,6 +29,24 @@ namespace dg {
 __device__ __forceinline__ void bar_state(int n) { asm volatile("bar.sync 2, %0;" ::"r"(n) : "memory"); }
 __device__ __forceinline__ void bar_lik(int n) { asm volatile("bar.sync 3, %0;" ::"r"(n) : "memory"); }
 
+// ---- thread-block cluster helpers (large genes: one chain over several SMs) ---------------
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store into the shared memory of block `rank` of the cluster (DSMEM), same offset as `p` here
+__device__ __forceinline__ void st_cluster(double *p, unsigned rank, double v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(dg_smem_u32(p)), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster(int *p, unsigned rank, int v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(dg_smem_u32(p)), "r"(rank));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
+
 // mantissa in [1,2) of a positive normal double whose high word is `hi`
 __device__ __forceinline__ double dg_mant(double x, int hi) {
     return __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
@@ -171,7 +189,7 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
 template <int KC, int J, int WMODE>
 __device__ __noinline__ void lik_warp_pass_log(const double *Wc, const int *rel, const int *ncnt, const int *cum,
                                                const double *ff, double *stage, double *red, int C, int Tc, int NWL,
-                                               int lane, int wl) {
+                                               int lane, int wl, int slots, int cs) {
     double mm[J], ls[J];
     int ee[J];
     unsigned bad = 0u;
@@ -183,7 +201,10 @@ __device__ __noinline__ void lik_warp_pass_log(const double *Wc, const int *rel,
         double v = ls[j];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0) red[j * DG_MAXWARPS + wl] = v;
+        if (lane == 0) {
+            if (cs == 1) red[j * slots + wl] = v;
+            else for (int r = 0; r < cs; ++r) st_cluster(red + j * slots + wl, r, v);
+        }
     }
 }
 
@@ -346,7 +367,7 @@ __device__ __noinline__ long long trace_page(int64_t *ptab, int step, int pshift
 // ---------------------------------------------------------------------------------------
 template <int KC, int WMODE, int D>
 __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArgs &sa, int chain,
-                          int slot, int n_steps, double *smem, int use_tma) {
+                          int slot, int n_steps, double *smem, int use_tma, int cs, int crank) {
     constexpr int J = (1 << D) - 1;
     constexpr int JP = J + 1;
     constexpr int SB = DG_STREAM_BLOCK;                   // stream steps produced per batch
@@ -354,14 +375,19 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     static_assert(SB >= 2 * D, "a stream batch must cover two rounds");
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-    if (ct.state[chain] != 0) return;                    // already finished (block-uniform)
 
     const int g = ct.gene[chain], t0 = ct.t0[chain];
     const int C = KC > 0 ? KC : gt.C[g];
     const int Tc = ct.Tc[chain], T = gt.T;
     const int CT = C * Tc, CTm = (C - 1) * Tc, RL = CT + 2;     // RL: doubles per stream ring row
     const int S = (CT + 31) >> 5, nstate = S << 5, NWL = nwarps - S;
-    const SmLayout L = dg_layout(C, Tc, nwarps, D);
+    // a cluster of cs blocks works on ONE chain: every block runs the same serial part (same
+    // inputs, same instructions, same results), the reads are split over all likelihood warps
+    // of the cluster, and the per-warp partial likelihoods are exchanged through distributed
+    // shared memory once per round.  Only block 0 writes the trace and the chain status.
+    const int SLOTS = cs > 1 ? DG_CLUSTER_SLOTS : DG_MAXWARPS;
+    const bool lead = crank == 0;
+    const SmLayout L = dg_layout(C, Tc, nwarps, D, cs);
     double *ycand = smem + L.ycand, *psic = smem + L.psic, *gs = smem + L.gs, *ex = smem + L.ex;
     double *pr = smem + L.pr, *ff = smem + L.ff, *zring = smem + L.zring, *dring = smem + L.dring;
     double *kinv = smem + L.kinv, *pfac = smem + L.pfac, *ijs = smem + L.ijs, *jcon = smem + L.jcon, *sqs = smem + L.sqs;
@@ -375,6 +401,8 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     const double prior_const = ct.prior_const[chain];
     const bool is_state = tid < nstate;
     const int wl = warp - S;                              // likelihood-warp index (>= 0 for those)
+    const int gwl = crank * NWL + wl, GW = cs * NWL;      // ... within the whole cluster
+    int xbuf = 0;                                         // exchange buffer (clusters double-buffer)
 
     const int32_t *roff = gt.roff + (size_t)g * (T + 1) + t0;
     const int r_first = roff[0];
@@ -565,7 +593,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             unsigned bad = 0u;
 #pragma unroll
             for (int j = 0; j < J; ++j) { mm[j] = 1.0; ee[j] = 0; lsd[j] = 0.0; }
-            lik_pass<KC, J, WMODE, false>(Wc, C, Tc, rel, ncnt, cum, ff, stage, lane, wl, NWL, mm, ee, bad, lsd);
+            lik_pass<KC, J, WMODE, false>(Wc, C, Tc, rel, ncnt, cum, ff, stage, lane, gwl, GW, mm, ee, bad, lsd);
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const int gg = __double2hiint(mm[j]);
@@ -582,13 +610,19 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                 bad |= __shfl_xor_sync(0xffffffffu, bad, off);
             }
             if (lane == 0) {
+                double *rd = red + xbuf * J * SLOTS;
+                int *ri = redi + xbuf * J * SLOTS;
+                int *rb = reinterpret_cast<int *>(redb) + xbuf * SLOTS;
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     const int gg = __double2hiint(mm[j]);
-                    red[j * DG_MAXWARPS + wl] = dg_mant(mm[j], gg);
-                    redi[j * DG_MAXWARPS + wl] = ee[j] + (gg >> 20) - 1023;
+                    const double mv = dg_mant(mm[j], gg);
+                    const int ev = ee[j] + (gg >> 20) - 1023;
+                    if (cs == 1) { rd[j * SLOTS + wl] = mv; ri[j * SLOTS + wl] = ev; }
+                    else for (int r = 0; r < cs; ++r) { st_cluster(rd + j * SLOTS + gwl, r, mv); st_cluster(ri + j * SLOTS + gwl, r, ev); }
                 }
-                redb[wl] = bad;
+                if (cs == 1) rb[wl] = (int)bad;
+                else for (int r = 0; r < cs; ++r) st_cluster(rb + gwl, r, (int)bad);
             }
         } else {
             if (s_act) {
@@ -624,7 +658,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             }
         }
         DG_TICK(1);
-        __syncthreads();                                                     // B2: partial likelihoods ready
+        if (cs == 1) __syncthreads(); else cluster_barrier();                // B2: partial likelihoods ready
         DG_TICK(2);
         // ================= decisions (warp 0; thread 0 walks the tree) =================
         bool redo = false;
@@ -635,12 +669,16 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                 if (!redo) {
                     double mm[J];
                     int ee[J];
+                    const double *rd = red + xbuf * J * SLOTS;
+                    const int *ri = redi + xbuf * J * SLOTS;
+                    const unsigned *rb = redb + xbuf * SLOTS;
 #pragma unroll
-                    for (int j = 0; j < J; ++j) {
-                        mm[j] = lane < NWL ? red[j * DG_MAXWARPS + lane] : 1.0;
-                        ee[j] = lane < NWL ? redi[j * DG_MAXWARPS + lane] : 0;
+                    for (int j = 0; j < J; ++j) { mm[j] = 1.0; ee[j] = 0; }
+                    for (int w = lane; w < GW; w += 32) {                    // <= 4 slots per lane: product < 16
+#pragma unroll
+                        for (int j = 0; j < J; ++j) { mm[j] *= rd[j * SLOTS + w]; ee[j] += ri[j * SLOTS + w]; }
+                        bad |= rb[w];
                     }
-                    bad = lane < NWL ? redb[lane] : 0u;
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
@@ -662,7 +700,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
                         double a = 0.0;
-                        for (int w = 0; w < NWL; ++w) a += red[j * DG_MAXWARPS + w];
+                        for (int w = 0; w < GW; ++w) a += red[xbuf * J * SLOTS + j * SLOTS + w];
                         lik[j] = a;
                     }
                 }
@@ -679,7 +717,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                         } else {
                             // trace pages of the rows this round may write (first touch allocates)
                             int nd_ok = nd_max;
-                            for (int d = 0; d < nd_max; ++d) {
+                            for (int d = 0; d < nd_max && lead; ++d) {
                                 const int step = m + d;
                                 if (page_cur < 0 || (step & pmask) == 0)
                                     page_cur = trace_page(ptab, step, pshift, rowlen, ct.pool_head, ct.pool_cap);
@@ -715,9 +753,12 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             }
             __syncthreads();                                                 // B3: decisions (or redo request)
             redo = bc[3] != 0.0;
+            if (cs > 1) xbuf ^= 1;
             if (redo) {                                                      // rare: some x_n was not a positive normal
-                if (!is_state) lik_warp_pass_log<KC, J, WMODE>(Wc, rel, ncnt, cum, ff, stage, red, C, Tc, NWL, lane, wl);
-                __syncthreads();
+                if (!is_state)
+                    lik_warp_pass_log<KC, J, WMODE>(Wc, rel, ncnt, cum, ff, stage, red + xbuf * J * SLOTS, C, Tc, GW, lane,
+                                                    gwl, SLOTS, cs);
+                if (cs == 1) __syncthreads(); else cluster_barrier();
             }
         } while (redo);
         DG_TICK(3);
@@ -727,7 +768,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         const bool nomem = bc[6] != 0.0;
         if (is_state) {
             if (s_act) {
-                for (int d = 0; d < nd; ++d) {
+                for (int d = 0; d < nd && lead; ++d) {
                     const int node = (int)bc[40 + d];
                     const int step = m + d;
                     double *row = ct.trace + __double_as_longlong(bc[32 + d]) + (size_t)(step & pmask) * rowlen;
@@ -761,7 +802,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         // [0, m-1) exclude the one just written
         const int mlast = m - 1;
         if (nd > 0 && mlast >= initial && (mlast % gap) == 0) {
-            __syncthreads();
+            if (cs == 1) __syncthreads(); else cluster_barrier();        // the lead block's rows are visible
             DG_TICK(4);
             const int conv = geweke_converged(gw, CTm, nwarps, warp, lane, tv, mlast);
             DG_TICK(5);
@@ -785,14 +826,16 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
 
     // ---- save state ------------------------------------------------------------------------
     __syncthreads();
-    if (s_act) { st[si] = y_now; st[CT + si] = psi_now; }
+    if (s_act && lead) { st[si] = y_now; st[CT + si] = psi_now; }
     if (tid == 0) {
-        st[2 * CT] = P_now; st[2 * CT + 1] = L_now;
-        ct.m_next[chain] = m;
-        ct.cnt[chain] = cnt;
-        ct.flags[chain] = flags;
-        ct.m_ret[chain] = m_ret;
-        ct.state[chain] = state;
+        if (lead) {
+            st[2 * CT] = P_now; st[2 * CT + 1] = L_now;
+            ct.m_next[chain] = m;
+            ct.cnt[chain] = cnt;
+            ct.flags[chain] = flags;
+            ct.m_ret[chain] = m_ret;
+            ct.state[chain] = state;
+        }
         if (W_IN_SMEM && use_tma)
             asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(dg_smem_u32(mbar)) : "memory");
     }

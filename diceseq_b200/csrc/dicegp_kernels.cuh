@@ -15,6 +15,7 @@
 #define DG_MAXCT 512          // C * Tc of one chain
 #define DG_MAXTHREADS 1024
 #define DG_MAXWARPS 32
+#define DG_CLUSTER_SLOTS 128   // likelihood warps of one chain spread over a thread-block cluster (<= 8 x 16)
 #define DG_GW_COLS 32         // Geweke column tile
 #define DG_STREAM_BLOCK 8      // random-stream steps produced per batch (ring = 2 batches)
 
@@ -96,8 +97,11 @@ struct SmLayout {
     int total;                                                 // doubles without W
 };
 
-__host__ __device__ inline SmLayout dg_layout(int C, int Tc, int nwarps, int D) {
+__host__ __device__ inline SmLayout dg_layout(int C, int Tc, int nwarps, int D, int cs = 1) {
     SmLayout L;
+    // partial-likelihood slots: one per likelihood warp of the chain; a cluster of cs blocks
+    // shares them (DG_CLUSTER_SLOTS) and double-buffers them across rounds
+    const int GWS = cs > 1 ? DG_CLUSTER_SLOTS : DG_MAXWARPS, NBUF = cs > 1 ? 2 : 1;
     const int J = (1 << D) - 1, JP = J + 1, RING = 2 * DG_STREAM_BLOCK;
     int CT = C * Tc, TT = Tc * Tc, o = 0;
     L.ycand = o; o += J * CT;  L.psic = o; o += J * CT;  L.gs = o; o += J * CT;  L.ex = o; o += J * CT;
@@ -107,9 +111,9 @@ __host__ __device__ inline SmLayout dg_layout(int C, int Tc, int nwarps, int D) 
     L.zring = o; o += DG_STREAM_BLOCK * (CT + 2);  L.dring = o; o += RING * (CT + 2);
     L.kinv = o; o += TT;  L.pfac = o; o += TT;
     L.ijs = o; o += C;    L.jcon = o; o += C;  L.sqs = o; o += C;
-    L.red = o; o += J * DG_MAXWARPS;
-    L.redi = o; o += J * DG_MAXWARPS / 2 + 1;  // ints
-    L.redb = o; o += DG_MAXWARPS / 2;          // unsigned
+    L.red = o; o += NBUF * J * GWS;
+    L.redi = o; o += NBUF * J * GWS / 2 + 1;   // ints
+    L.redb = o; o += NBUF * GWS / 2;           // unsigned
     L.bc = o; o += 64;
     { const int ctm = CT - Tc; L.gw = o; o += 2 * nwarps * (ctm < DG_GW_COLS ? (ctm > 0 ? ctm : 1) : DG_GW_COLS); }
     L.rel = o; o += Tc + 2;                    // ints: rel roff[Tc+1], ncnt[Tc]
