@@ -135,3 +135,19 @@ def test_small_chunks_equal_large_chunks():
     b = Psi_GP_MH(R, L, P, max_chunk=37, **kw)
     assert a[6] == b[6] and a[5] == b[5]
     assert np.array_equal(a[3], b[3]) and np.array_equal(a[1], b[1])
+
+
+def test_large_gene_takes_cluster_tier_and_matches_oracle():
+    """Human-scale tail (BASELINE config 5): 20 isoforms, 60k reads at one of 2 time points
+    (W = 10 MB -> cluster of 4 blocks by default), generic-C kernel with plain global loads."""
+    rng = np.random.RandomState(77)
+    R, L, P = synth.gene_matrices("timeseries", 27, reads=60000, T=1, C=20)
+    R2, L2, P2 = synth.gene_matrices("timeseries", 28, reads=3001, T=1, C=20)
+    R, L, P = R + R2, L + L2, P + P2
+    kw = dict(theta1=3.0, theta2=float(synth.default_theta2(np.arange(2))), M=60, initial=40, gap=10,
+              var=0.002 * np.ones(19), randomS=5)
+    with np.errstate(all="ignore"):
+        ref = orc.psi_gp_mh([r.copy() for r in R], [l.copy() for l in L], [p.copy() for p in P], **kw)
+    got = Psi_GP_MH(R, L, P, **kw)
+    compare(got, ref)
+    assert got[5] > 0
