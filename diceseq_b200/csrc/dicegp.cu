@@ -32,14 +32,14 @@ constexpr int DICEGP_CHAIN_NOMEM_ = 3;
 #ifndef DG_SPEC_DEPTH
 #define DG_SPEC_DEPTH 2                  // MH steps decided per pass over W (speculation tree depth)
 #endif
-template <int KC, int WMODE>
+template <int KC, int WMODE, bool CLUSTER = false>
 __global__ void __launch_bounds__(DG_LB_THREADS, 1)
 dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__restrict__ ids, int n_ids,
                     int n_steps, int use_tma, int *queue) {
     extern __shared__ __align__(128) double dg_smem[];
     __shared__ int next_slot;
     // cluster launch (large genes): the blocks of a cluster work on the same chain
-    const int cs = (int)dg::cluster_size(), crank = (int)dg::cluster_rank();
+    const int cs = CLUSTER ? (int)dg::cluster_size() : 1, crank = CLUSTER ? (int)dg::cluster_rank() : 0;
     int slot = blockIdx.x / cs;
     while (true) {
         if (queue != nullptr) {
@@ -62,7 +62,7 @@ dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__res
         // every block of the cluster reads the chain state BEFORE the lead block may change it
         const bool running = ct.state[ids[slot]] == 0;
         if (cs > 1) dg::cluster_barrier();
-        if (running) dg::run_chain<KC, WMODE, DG_SPEC_DEPTH>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma, cs, crank);
+        if (running) dg::run_chain<KC, WMODE, DG_SPEC_DEPTH, CLUSTER>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma, cs, crank);
         if (cs == 1) __syncthreads(); else dg::cluster_barrier();
         if (queue == nullptr) break;
     }
@@ -510,8 +510,21 @@ int preallocate_trace_pages(dicegp_ctx *c, const std::vector<int32_t> &ids) {
 }
 
 typedef void (*chain_kernel_t)(GeneTab, ChainTab, StreamArgs, const int32_t *, int, int, int, int *);
-chain_kernel_t chain_kernel_for(int kind, bool w_in_smem) {
-    // streamed W: staged through cp.async for compiled isoform counts, plain loads otherwise
+chain_kernel_t chain_kernel_for(int kind, bool w_in_smem, bool cluster) {
+    // streamed W: staged through cp.async for compiled isoform counts, plain loads otherwise;
+    // cluster launches exist for the streamed variants only
+    if (cluster) {
+        switch (kind) {
+            case 0: return dicegp_chain_kernel<0, dg::W_DIRECT, true>;
+            case 1: return dicegp_chain_kernel<2, dg::W_STAGED, true>;
+            case 2: return dicegp_chain_kernel<3, dg::W_STAGED, true>;
+            case 3: return dicegp_chain_kernel<4, dg::W_STAGED, true>;
+            case 4: return dicegp_chain_kernel<5, dg::W_STAGED, true>;
+            case 5: return dicegp_chain_kernel<6, dg::W_STAGED, true>;
+            case 6: return dicegp_chain_kernel<7, dg::W_STAGED, true>;
+            default: return dicegp_chain_kernel<8, dg::W_STAGED, true>;
+        }
+    }
     switch (kind * 2 + (w_in_smem ? 1 : 0)) {
         case 0: return dicegp_chain_kernel<0, dg::W_DIRECT>;   case 1: return dicegp_chain_kernel<0, dg::W_RESIDENT>;
         case 2: return dicegp_chain_kernel<2, dg::W_STAGED>;   case 3: return dicegp_chain_kernel<2, dg::W_RESIDENT>;
@@ -681,7 +694,9 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                 queue = c->dqueue.p + k;
             }
             grid *= cs;
-            chain_kernel_t kern = chain_kernel_for(kind, cls[tier].w_in_smem);
+            // the streamed tiers all use the cluster-capable variants (cluster size 1 for tier 4): their code
+            // schedule is also the faster one for a single block (measured)
+            chain_kernel_t kern = chain_kernel_for(kind, cls[tier].w_in_smem, tier >= 4);
             DG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(c->smem_optin - c->static_smem)));
             {
@@ -775,8 +790,8 @@ int dicegp_create(int device, dicegp_ctx **out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     {
         cudaFuncAttributes fa0, fa1;
-        if (cudaFuncGetAttributes(&fa0, dicegp_chain_kernel<0, dg::W_DIRECT>) != cudaSuccess ||
-            cudaFuncGetAttributes(&fa1, dicegp_chain_kernel<0, dg::W_RESIDENT>) != cudaSuccess) {
+        if (cudaFuncGetAttributes(&fa0, dicegp_chain_kernel<0, dg::W_DIRECT, false>) != cudaSuccess ||
+            cudaFuncGetAttributes(&fa1, dicegp_chain_kernel<0, dg::W_RESIDENT, false>) != cudaSuccess) {
             g_last_error = std::string("kernel image not loadable on this device: ") + cudaGetErrorString(cudaGetLastError());
             delete c;
             return DICEGP_ERR_CUDA;

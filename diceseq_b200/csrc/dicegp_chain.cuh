@@ -120,6 +120,7 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
                 for (int j = 0; j < J; ++j) fr[k][j] = ffcol[k * JP + j];
             }
         }
+#pragma unroll(WMODE == W_STAGED ? 2 : 1)
         for (; q < c1; q += NWL, ++it) {
             const int p = (q - c0) * 32 + lane;
             if (WMODE == W_STAGED) {
@@ -365,9 +366,10 @@ __device__ __noinline__ long long trace_page(int64_t *ptab, int step, int pshift
 // ---------------------------------------------------------------------------------------
 // one chain, up to n_steps steps.  `slot` indexes the host stream blocks.
 // ---------------------------------------------------------------------------------------
-template <int KC, int WMODE, int D>
+template <int KC, int WMODE, int D, bool CLUSTER>
 __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArgs &sa, int chain,
-                          int slot, int n_steps, double *smem, int use_tma, int cs, int crank) {
+                          int slot, int n_steps, double *smem, int use_tma, int cs_rt, int crank_rt) {
+    const int cs = CLUSTER ? cs_rt : 1, crank = CLUSTER ? crank_rt : 0;   // compile-time 1 / 0 for ordinary launches
     constexpr int J = (1 << D) - 1;
     constexpr int JP = J + 1;
     constexpr int SB = DG_STREAM_BLOCK;                   // stream steps produced per batch
