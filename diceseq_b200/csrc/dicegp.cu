@@ -543,7 +543,7 @@ chain_kernel_t chain_kernel_for(int kind, bool w_in_smem, bool cluster) {
 // latency_mode: few chains are left (the stragglers of a batch); give each as many likelihood
 // warps as fit instead of packing many chains per SM.
 int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, StreamArgs sa,
-               const std::vector<int64_t> *delta_off, bool persistent, bool latency_mode = false) {
+               const std::vector<int64_t> *delta_off, bool persistent, int latency_mode = 0) {
     LaunchClass cls[kTiers];
     launch_classes(c, cls);
     if (latency_mode) {
@@ -555,6 +555,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
         const dicegp_chain_desc &d = c->hdesc[ids[i]];
         const int C = c->hC[d.gene];
         int tier = pick_tier(c, cls, ids[i]);
+        if (latency_mode == 2 && tier == 4) tier = 6;          // last stragglers: a cluster of 4 blocks each
         const int k = tier * kKinds + kind_of(C);
         by_group[k].push_back(ids[i]);
         slot_src[k].push_back((int32_t)i);
@@ -1117,26 +1118,40 @@ int dicegp_run_device_stream(dicegp_ctx *c, uint64_t seed, const int64_t *stream
     // shapes): the few chains still running -- they would otherwise crawl along with the two or
     // three likelihood warps of the throughput shape while the rest of the GPU idles.  The
     // stream is counter based, so a resumed chain continues bit-identically.
-    const int kStragglerSteps = 4096;
-    const char *env_cap = getenv("DICEGP_STRAGGLER_STEPS");
-    const int cap = env_cap ? atoi(env_cap) : kStragglerSteps;
-    if (cap <= 0 || max_M <= cap) return run_chains(c, ids, max_M, sa, nullptr, true);
-    int rc = run_chains(c, ids, cap, sa, nullptr, true);
-    if (rc != DICEGP_OK) return rc;
-    const double ms1 = c->last_ms;
-    const int64_t l1 = c->last_launches, e1 = c->last_evals, s1 = c->last_steps;
-    std::vector<int32_t> st(c->n_chains);
-    DG_CUDA(c, cudaMemcpy(st.data(), c->cstate.p, c->n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    std::vector<int32_t> rest;
-    for (int i = 0; i < c->n_chains; ++i) if (st[i] == DICEGP_CHAIN_RUNNING) rest.push_back(i);
-    if (!rest.empty()) {
-        rc = run_chains(c, rest, max_M, sa, nullptr, true, true);
+    // Pass 1 (throughput shapes): every chain, capped at 4096 steps.  Pass 2 (latency shapes,
+    // one chain per SM with as many likelihood warps as fit): the ~10% of chains still running.
+    // Otherwise a handful of non-converging chains would crawl along with two likelihood warps
+    // each while the rest of the GPU idles.  The stream is counter based, so a resumed chain
+    // continues bit-identically.  (An optional third pass on clusters of 4 blocks exists for
+    // experiments -- DICEGP_STRAGGLER_STEPS=a,b -- but measured slower on the bench workload.)
+    int cap0 = 4096, cap1 = 0;
+    if (const char *e = getenv("DICEGP_STRAGGLER_STEPS")) sscanf(e, "%d,%d", &cap0, &cap1);
+    if (cap0 <= 0 || max_M <= cap0) return run_chains(c, ids, max_M, sa, nullptr, true, 0);
+    std::vector<std::pair<int, int>> plan;                      // (absolute step cap, shape mode)
+    plan.push_back({cap0, 0});
+    if (cap1 > cap0 && cap1 < max_M) { plan.push_back({cap1, 1}); plan.push_back({max_M, 2}); }
+    else plan.push_back({max_M, 1});
+    double ms = 0.0;
+    int64_t launches = 0, evals = 0, steps = 0;
+    std::vector<int32_t> todo = ids;
+    int prev = 0;                                               // steps every chain in `todo` has done
+    for (size_t pass = 0; pass < plan.size() && !todo.empty(); ++pass) {
+        const int cap = plan[pass].first;
+        int rc = run_chains(c, todo, cap - prev, sa, nullptr, true, plan[pass].second);
         if (rc != DICEGP_OK) return rc;
+        prev = cap;
         if (getenv("DICEGP_VERBOSE"))
-            fprintf(stderr, "[dicegp] pass1 %.1f ms (%lld steps, %d chains)  pass2 %.1f ms (%lld steps, %zu chains)\n", ms1,
-                    (long long)s1, c->n_chains, c->last_ms, (long long)c->last_steps, rest.size());
-        c->last_ms += ms1; c->last_launches += l1; c->last_evals += e1; c->last_steps += s1;
+            fprintf(stderr, "[dicegp] pass %zu (cap %d, mode %d): %.1f ms, %lld steps, %zu chains\n", pass, cap,
+                    plan[pass].second, c->last_ms, (long long)c->last_steps, todo.size());
+        ms += c->last_ms; launches += c->last_launches; evals += c->last_evals; steps += c->last_steps;
+        if (cap >= max_M) break;
+        std::vector<int32_t> st(c->n_chains);
+        DG_CUDA(c, cudaMemcpy(st.data(), c->cstate.p, c->n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        std::vector<int32_t> rest;
+        for (int32_t id : todo) if (st[id] == DICEGP_CHAIN_RUNNING) rest.push_back(id);
+        todo.swap(rest);
     }
+    c->last_ms = ms; c->last_launches = launches; c->last_evals = evals; c->last_steps = steps;
     return DICEGP_OK;
 }
 
