@@ -145,7 +145,7 @@ def run_reference(args, wl):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_genes = max(cores, 8)
+    n_genes = max(2 * cores, 16)
     for w in range(args.warmup):
         cpu_sample(wl["config"], wl["T"], min(n_genes, cores), 900000 + w * n_genes, cores)
     evals = genes = 0
@@ -218,7 +218,7 @@ def run_ours(args, wl):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # before any CUDA work in this process: the worker pool is forked
         cores = os.cpu_count() or 1
-        n = max(cores, 8)
+        n = max(4 * cores, 32)                      # ~15-20 s of CPU work on all cores
         e, g, dt = cpu_sample(wl["config"], T, n, 2000000, cores)
         cpu_line = {"value": e / dt, "unit": "evals/s", "genes_per_s": g / dt, "cores": cores, "kind": "port",
                     "sample": "%d genes of the same workload, multiprocessing.Pool(%d), oracle port with the "
