@@ -532,6 +532,12 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     for (int i = 0; i < 10; ++i) dg_prof[i] = 0;
 #endif
 
+    // Shape of the speculation tree for J = 3 candidates (uniform over the block, may change
+    // between rounds): 0 = full depth-2 tree {A, B|A rejected, B'|A accepted}: always 2 steps per
+    // round; 1 = rejection chain {A, B|A rej., C|A,B rej.}: 1 + (1-p) + (1-p)^2 steps per round,
+    // better when the acceptance rate p is below 0.38 (time-series genes run at ~0.16).
+    constexpr int DM = (J == 3) ? 3 : D;                  // most steps a round can commit
+    int shape = (J == 3 && m > 0 && ct.cnt[chain] * 20 < m * 7) ? 1 : 0;
     bool init = (m == 0);                                 // evaluate the start value first (model_GP.py:275-292)
     // next convergence-check step at or after m (m >= initial and m % gap == 0)
     int next_check = m > initial ? m : initial;
@@ -539,7 +545,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     int rbase = m % RING;                                 // ring slot of step m
     while (m < m_end || init) {
         // steps this round may commit: up to D, not past the chunk, not past a check step
-        const int nd_max = init ? 0 : min(D, min(m_end - m, next_check - m + 1));
+        const int nd_max = init ? 0 : min(shape ? DM : D, min(m_end - m, next_check - m + 1));
         // ================= S phase (state warps): candidates -> f =================
         double yj[J], bj[J], ej[J], gj[J];
         if (is_state) {
@@ -549,9 +555,9 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
 #pragma unroll
                     for (int j = 0; j < J; ++j) { yj[j] = v; bj[j] = v; }
                 } else if (s_free) {
-                    double dl[D];                                            // increments of steps m .. m+D-1
+                    double dl[DM];                                           // increments of steps m .. m+DM-1
 #pragma unroll
-                    for (int d = 0; d < D; ++d) {
+                    for (int d = 0; d < DM; ++d) {
                         int sl = rbase + d;
                         if (sl >= RING) sl -= RING;
                         dl[d] = d < nd_max ? dring[sl * RL + si] : 0.0;
@@ -563,7 +569,9 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                         const int dep = (j >= 3) ? 2 : (j >= 1 ? 1 : 0);
                         if (j == 0) bj[j] = y_now;
                         else bj[j] = (j & 1) ? bj[(j - 1) / 2] : yj[(j - 1) / 2];   // odd = parent rejected
-                        yj[j] = dl[dep] + bj[j];
+                        double dj = dl[dep];
+                        if (J == 3 && j == 2 && shape) { bj[j] = y_now; dj = dl[DM - 1]; }   // chain: third proposal after two rejections
+                        yj[j] = dj + bj[j];
                     }
                 } else {
 #pragma unroll
@@ -728,7 +736,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                             }
                             // walk the tree: alpha = exp(min(a, 0)), accept iff u < alpha (:348-351),
                             // tested in the log domain with log(u) taken off the critical path
-                            int node = 0, cur = -1;
+                            int node = 0, cur = -1, nd_done = nd_ok;
                             for (int d = 0; d < nd_ok; ++d) {
                                 double likn = lik[0], priorn = bc[16 + node];
 #pragma unroll
@@ -744,11 +752,19 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                                 bc[40 + d] = (double)cur;                    // state after step m+d
                                 bc[48 + d] = P_now;                          // Pro_all[m+d]  (:362)
                                 bc[56 + d] = L_now;                          // Lik_all[m+d]  (:363)
-                                node = 2 * node + (acc ? 2 : 1);
+                                if (shape) {                                 // chain: later candidates assumed this rejection
+                                    if (acc) { nd_done = d + 1; break; }
+                                    node = d + 1;
+                                } else {
+                                    node = 2 * node + (acc ? 2 : 1);
+                                }
                             }
-                            bc[4] = (double)nd_ok;
+                            bc[4] = (double)nd_done;
                             bc[5] = (double)cur;
                             bc[6] = (nd_ok < nd_max) ? 1.0 : 0.0;            // trace pool exhausted
+                            // shape of the next round from the running acceptance rate (p < 0.35 -> chain)
+                            const int m_new = m + nd_done;
+                            bc[7] = (J == 3 && m_new >= 64 && cnt * 20 < m_new * 7) ? 1.0 : 0.0;
                         }
                     }
                 }
@@ -767,6 +783,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         // ================= update + trace rows (state warps) || stream refill (others) ======
         const int nd = (int)bc[4];
         const int fin = (int)bc[5];
+        const int shape_next = init ? shape : (int)bc[7];
         const bool nomem = bc[6] != 0.0;
         if (is_state) {
             if (s_act) {
@@ -792,6 +809,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         }
         if (!init && produced < m_end && produced - (m + nd) <= SB) produced = min(produced + SB, m_end);
         if (init) { init = false; continue; }
+        shape = shape_next;
         m += nd;
         rbase += nd;
         if (rbase >= RING) rbase -= RING;
