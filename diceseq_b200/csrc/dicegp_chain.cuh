@@ -536,8 +536,13 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     // between rounds): 0 = full depth-2 tree {A, B|A rejected, B'|A accepted}: always 2 steps per
     // round; 1 = rejection chain {A, B|A rej., C|A,B rej.}: 1 + (1-p) + (1-p)^2 steps per round,
     // better when the acceptance rate p is below 0.38 (time-series genes run at ~0.16).
-    constexpr int DM = (J == 3) ? 3 : D;                  // most steps a round can commit
-    int shape = (J == 3 && m > 0 && ct.cnt[chain] * 20 < m * 7) ? 1 : 0;
+#ifdef DG_NO_CHAIN
+    constexpr bool kChain = false;
+#else
+    constexpr bool kChain = (J == 3);
+#endif
+    constexpr int DM = kChain ? 3 : D;                    // most steps a round can commit
+    int shape = (kChain && m > 0 && ct.cnt[chain] * 20 < m * 7) ? 1 : 0;
     bool init = (m == 0);                                 // evaluate the start value first (model_GP.py:275-292)
     // next convergence-check step at or after m (m >= initial and m % gap == 0)
     int next_check = m > initial ? m : initial;
@@ -570,7 +575,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                         if (j == 0) bj[j] = y_now;
                         else bj[j] = (j & 1) ? bj[(j - 1) / 2] : yj[(j - 1) / 2];   // odd = parent rejected
                         double dj = dl[dep];
-                        if (J == 3 && j == 2 && shape) { bj[j] = y_now; dj = dl[DM - 1]; }   // chain: third proposal after two rejections
+                        if (kChain && j == 2 && shape) { bj[j] = y_now; dj = dl[DM - 1]; }   // chain: third proposal after two rejections
                         yj[j] = dj + bj[j];
                     }
                 } else {
@@ -759,12 +764,15 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                                     node = 2 * node + (acc ? 2 : 1);
                                 }
                             }
+                            // a chain round that stopped early leaves the page cursor on its last
+                            // committed row (the pages of the unused rows stay allocated for later)
+                            if (nd_done > 0 && nd_done < nd_ok && lead) page_cur = __double_as_longlong(bc[32 + nd_done - 1]);
                             bc[4] = (double)nd_done;
                             bc[5] = (double)cur;
                             bc[6] = (nd_ok < nd_max) ? 1.0 : 0.0;            // trace pool exhausted
                             // shape of the next round from the running acceptance rate (p < 0.35 -> chain)
                             const int m_new = m + nd_done;
-                            bc[7] = (J == 3 && m_new >= 64 && cnt * 20 < m_new * 7) ? 1.0 : 0.0;
+                            bc[7] = (kChain && m_new >= 64 && cnt * 20 < m_new * 7) ? 1.0 : 0.0;
                         }
                     }
                 }

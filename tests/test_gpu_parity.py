@@ -94,6 +94,23 @@ def test_step_parity_with_oracle(shape):
     compare(got, ref)
 
 
+@pytest.mark.parametrize("g", [20, 56, 94, 146, 149, 184])
+def test_low_acceptance_rounds_across_trace_pages(g):
+    """Wide proposals (acceptance ~0.15) put the kernel into its rejection-chain rounds, which
+    commit 1-3 steps each; the run crosses the 1024-row trace pages at every alignment and
+    the convergence checks read those rows back."""
+    rs = np.random.RandomState(g)
+    T = int(rs.choice([1, 3, 4, 8])); C = int(rs.choice([2, 3, 4, 6, 8])); reads = int(rs.choice([200, 999, 2000]))
+    R, L, P = synth.gene_matrices("timeseries", g, reads=reads, T=T, C=C)
+    kw = dict(theta1=3.0, theta2=float(synth.default_theta2(np.arange(T))), M=2500, initial=1000, gap=100,
+              randomS=7 + g, var=0.15 * np.ones(C - 1))
+    with np.errstate(all="ignore"):
+        ref = orc.psi_gp_mh([r.copy() for r in R], [l.copy() for l in L], [p.copy() for p in P], **kw)
+    got = Psi_GP_MH(R, L, P, **kw)
+    assert ref[5] < 0.35 * ref[6]
+    compare(got, ref)
+
+
 def test_pipeline_prerun_variance_and_main(golden):
     """get_psi's sampler logic (pre-runs -> var -> joint run) with the product sampler
     plugged into the oracle's driver restatement reproduces the reference run."""
