@@ -29,10 +29,16 @@ constexpr int DICEGP_CHAIN_NOMEM_ = 3;
 #ifndef DG_LB_THREADS
 #define DG_LB_THREADS 512                // 512 threads/SM -> up to 128 registers per thread
 #endif
-#ifndef DG_SPEC_DEPTH
-#define DG_SPEC_DEPTH 2                  // MH steps decided per pass over W (speculation tree depth)
+// Candidate nodes evaluated per round (= per pass over W).  Resident tiers are bound by the
+// serial part of a round: 3 nodes.  Streamed tiers are bound by the bytes of W they pull from
+// L2 / HBM every round: 6 nodes commit more steps per byte.
+#ifndef DG_NODES_RESIDENT
+#define DG_NODES_RESIDENT 3
 #endif
-template <int KC, int WMODE, bool CLUSTER = false>
+#ifndef DG_NODES_STREAMED
+#define DG_NODES_STREAMED 3
+#endif
+template <int KC, int WMODE, bool CLUSTER = false, int NJ = DG_NODES_RESIDENT>
 __global__ void __launch_bounds__(DG_LB_THREADS, 1)
 dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__restrict__ ids, int n_ids,
                     int n_steps, int use_tma, int *queue) {
@@ -62,7 +68,7 @@ dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__res
         // every block of the cluster reads the chain state BEFORE the lead block may change it
         const bool running = ct.state[ids[slot]] == 0;
         if (cs > 1) dg::cluster_barrier();
-        if (running) dg::run_chain<KC, WMODE, DG_SPEC_DEPTH, CLUSTER>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma, cs, crank);
+        if (running) dg::run_chain<KC, WMODE, NJ, CLUSTER>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, use_tma, cs, crank);
         if (cs == 1) __syncthreads(); else dg::cluster_barrier();
         if (queue == nullptr) break;
     }
@@ -441,8 +447,9 @@ void launch_classes(const dicegp_ctx *c, LaunchClass out[kTiers]) {
     }
 }
 
-size_t fixed_smem_bytes(int C, int Tc, int threads, int cs = 1) {
-    return (size_t)dg_layout(C, Tc, (threads + 31) / 32, DG_SPEC_DEPTH, cs).total * sizeof(double);
+// shared memory of a chain besides W / the staging rings; `streamed`: tiers 4-7
+size_t fixed_smem_bytes(int C, int Tc, int threads, bool streamed, int cs = 1) {
+    return (size_t)dg_layout(C, Tc, (threads + 31) / 32, streamed ? DG_NODES_STREAMED : DG_NODES_RESIDENT, cs).total * sizeof(double);
 }
 inline int tier_cluster(int tier) { return tier < 5 ? 1 : (2 << (tier - 5)); }
 
@@ -475,7 +482,7 @@ int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain) {
     if (wb >= wide_min) return 5;
     for (int i = 0; i < 4; ++i) {
         if (cls[i].threads < min_threads(C, d.Tc)) continue;
-        if (fixed_smem_bytes(C, d.Tc, cls[i].threads) + (size_t)wb <= cls[i].smem_limit) return i;
+        if (fixed_smem_bytes(C, d.Tc, cls[i].threads, false) + (size_t)wb <= cls[i].smem_limit) return i;
     }
     return 4;
 }
@@ -515,25 +522,26 @@ chain_kernel_t chain_kernel_for(int kind, bool w_in_smem, bool cluster) {
     // cluster launches exist for the streamed variants only
     if (cluster) {
         switch (kind) {
-            case 0: return dicegp_chain_kernel<0, dg::W_DIRECT, true>;
-            case 1: return dicegp_chain_kernel<2, dg::W_STAGED, true>;
-            case 2: return dicegp_chain_kernel<3, dg::W_STAGED, true>;
-            case 3: return dicegp_chain_kernel<4, dg::W_STAGED, true>;
-            case 4: return dicegp_chain_kernel<5, dg::W_STAGED, true>;
-            case 5: return dicegp_chain_kernel<6, dg::W_STAGED, true>;
-            case 6: return dicegp_chain_kernel<7, dg::W_STAGED, true>;
-            default: return dicegp_chain_kernel<8, dg::W_STAGED, true>;
+            case 0: return dicegp_chain_kernel<0, dg::W_DIRECT, true, DG_NODES_STREAMED>;
+            case 1: return dicegp_chain_kernel<2, dg::W_STAGED, true, DG_NODES_STREAMED>;
+            case 2: return dicegp_chain_kernel<3, dg::W_STAGED, true, DG_NODES_STREAMED>;
+            case 3: return dicegp_chain_kernel<4, dg::W_STAGED, true, DG_NODES_STREAMED>;
+            case 4: return dicegp_chain_kernel<5, dg::W_STAGED, true, DG_NODES_STREAMED>;
+            case 5: return dicegp_chain_kernel<6, dg::W_STAGED, true, DG_NODES_STREAMED>;
+            case 6: return dicegp_chain_kernel<7, dg::W_STAGED, true, DG_NODES_STREAMED>;
+            default: return dicegp_chain_kernel<8, dg::W_STAGED, true, DG_NODES_STREAMED>;
         }
     }
-    switch (kind * 2 + (w_in_smem ? 1 : 0)) {
-        case 0: return dicegp_chain_kernel<0, dg::W_DIRECT>;   case 1: return dicegp_chain_kernel<0, dg::W_RESIDENT>;
-        case 2: return dicegp_chain_kernel<2, dg::W_STAGED>;   case 3: return dicegp_chain_kernel<2, dg::W_RESIDENT>;
-        case 4: return dicegp_chain_kernel<3, dg::W_STAGED>;   case 5: return dicegp_chain_kernel<3, dg::W_RESIDENT>;
-        case 6: return dicegp_chain_kernel<4, dg::W_STAGED>;   case 7: return dicegp_chain_kernel<4, dg::W_RESIDENT>;
-        case 8: return dicegp_chain_kernel<5, dg::W_STAGED>;   case 9: return dicegp_chain_kernel<5, dg::W_RESIDENT>;
-        case 10: return dicegp_chain_kernel<6, dg::W_STAGED>;  case 11: return dicegp_chain_kernel<6, dg::W_RESIDENT>;
-        case 12: return dicegp_chain_kernel<7, dg::W_STAGED>;  case 13: return dicegp_chain_kernel<7, dg::W_RESIDENT>;
-        case 14: return dicegp_chain_kernel<8, dg::W_STAGED>;  default: return dicegp_chain_kernel<8, dg::W_RESIDENT>;
+    (void)w_in_smem;
+    switch (kind) {
+        case 0: return dicegp_chain_kernel<0, dg::W_RESIDENT>;
+        case 1: return dicegp_chain_kernel<2, dg::W_RESIDENT>;
+        case 2: return dicegp_chain_kernel<3, dg::W_RESIDENT>;
+        case 3: return dicegp_chain_kernel<4, dg::W_RESIDENT>;
+        case 4: return dicegp_chain_kernel<5, dg::W_RESIDENT>;
+        case 5: return dicegp_chain_kernel<6, dg::W_RESIDENT>;
+        case 6: return dicegp_chain_kernel<7, dg::W_RESIDENT>;
+        default: return dicegp_chain_kernel<8, dg::W_RESIDENT>;
     }
 }
 
@@ -637,7 +645,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                     for (int nwl = 2; nwl <= 14; ++nwl) {
                         const int thr = 32 * (maxS + nwl);
                         if (thr * kk > DG_LB_THREADS) continue;
-                        size_t need = fixed_smem_bytes(maxC, maxTc, thr) + 1024;
+                        size_t need = fixed_smem_bytes(maxC, maxTc, thr, true) + 1024;
                         if (kind != 0) need += (size_t)nwl * dg::kStages * maxC * 512;
                         if (need * kk > 233472) continue;
                         // at least 8 streaming warps per SM, then as many chains as possible (their serial
@@ -654,7 +662,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                 for (int nwl = 2; nwl <= 14; ++nwl) {
                     const int thr = 32 * (maxS + nwl);
                     if (thr > DG_LB_THREADS) break;
-                    size_t need = fixed_smem_bytes(maxC, maxTc, thr, cs) + 1024;
+                    size_t need = fixed_smem_bytes(maxC, maxTc, thr, true, cs) + 1024;
                     if (kind != 0) need += (size_t)nwl * dg::kStages * maxC * 512;
                     if (need > 233472) break;
                     best = thr;
@@ -668,7 +676,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             size_t smem = 0;
             for (int32_t id : by_group[k]) {
                 const dicegp_chain_desc &d = c->hdesc[id];
-                size_t need = fixed_smem_bytes(c->hC[d.gene], d.Tc, threads, cs);
+                size_t need = fixed_smem_bytes(c->hC[d.gene], d.Tc, threads, tier >= 4, cs);
                 if (cls[tier].w_in_smem) need += (size_t)chain_wbytes(c, id);
                 else if (kind != 0) {
                     // per likelihood warp: kStages x C x 32 lanes x 16 bytes of cp.async staging
@@ -946,7 +954,7 @@ static int install_chains(dicegp_ctx *c, int32_t n, const dicegp_chain_desc *des
         for (int k = 1; k < n_pages; ++k) ptab.push_back(-1);
         tr += rowlen << shift;
         worst += (rowlen << shift) * n_pages;
-        st += rowlen;
+        st += rowlen + dg::dg_geweke_state_len((C - 1) * d.Tc);     // resume state + running Geweke sums
     }
 #define DG_RESIZE(buf, cnt) if ((buf).resize(cnt) != cudaSuccess) return c->fail(DICEGP_ERR_NOMEM, "set_chains: device allocation failed (" #buf ")")
     DG_RESIZE(c->cgene, n); DG_RESIZE(c->ct0, n); DG_RESIZE(c->cTc, n); DG_RESIZE(c->cM, n);

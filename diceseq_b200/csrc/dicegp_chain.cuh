@@ -80,7 +80,7 @@ template <int KC, int J, int WMODE, bool LOGPATH>
 __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, int Tc, const int *rel, const int *ncnt,
                                          const int *cum, const double *ff, double *stage, int lane, int wl, int NWL,
                                          double (&mm)[J], int (&ee)[J], unsigned &bad, double (&ls)[J]) {
-    constexpr int JP = J + 1;
+    constexpr int JP = (J + 1) & ~1;
     const int nitems = cum[Tc];
     const int kmax = KC > 0 ? KC : C;
     double2 *mystage = reinterpret_cast<double2 *>(stage) + lane;     // [stage][k][32 lanes]
@@ -103,7 +103,7 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
 #pragma unroll
         for (int s = 0; s < kStages - 1; ++s) issue(s);
     }
-    constexpr bool FREG = (KC > 0 && KC * J <= 24);                   // f of the time point held in registers
+    constexpr bool FREG = (KC > 0 && KC * J <= (J > 3 ? 18 : 24));                  // f of the time point held in registers
     constexpr int FR = FREG ? KC : 1;
     int it = 0, q = wl;
     for (int tt = 0; tt < Tc; ++tt) {
@@ -120,7 +120,7 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
                 for (int j = 0; j < J; ++j) fr[k][j] = ffcol[k * JP + j];
             }
         }
-#pragma unroll(WMODE == W_STAGED ? 2 : 1)
+#pragma unroll((WMODE == W_STAGED && J <= 3) ? 2 : 1)
         for (; q < c1; q += NWL, ++it) {
             const int p = (q - c0) * 32 + lane;
             if (WMODE == W_STAGED) {
@@ -211,58 +211,86 @@ __device__ __noinline__ void lik_warp_pass_log(const double *Wc, const int *rel,
 
 // ---------------------------------------------------------------------------------------
 // Geweke convergence rule over trace rows [0, m)          model_GP.py:156-185, :369-391
-// Series = Psi_all[:m, c, t] for c < C-1 (columns 0..CTm-1 of a trace row).
-// Two-pass mean / population variance like np.mean / np.var.  Lanes walk columns
-// (coalesced), warps walk rows.  Returns 1 to every thread when all |Z| <= 2.
+// Series = Psi_all[:m, c, t] for c < C-1 (columns 0..CTm-1 of a trace row); window A = rows
+// [0, int(0.1 m)), window B = rows [int(0.5 m), m); converged when every column has
+// |mean_A - mean_B| / sqrt(var_A + var_B) <= 2 (population variances, np.var).
+//
+// The windows only grow and slide between checks, so the chain keeps, per column, running
+// sums over both windows of d = x - K and d^2 (K = the column's value in row int(0.5 m) of
+// the first check: a post-burn-in value, which keeps var = Q/n - (S/n)^2 free of
+// cancellation) and a check touches only the rows that entered or left a window
+// (~1.6 gap rows) instead of all 0.6 m rows twice.  Lanes walk columns (coalesced), warps
+// walk rows.  The sums live in global memory behind the chain's resume state, so a chain
+// cut into several launches sees the same operations as an uncut one.
+//   gst[0] rows in window A, gst[1] / gst[2] first / end row of window B, gst[3] K is set,
+//   then K, S_A, Q_A, S_B, Q_B (CTm doubles each).
+// Returns 1 to every thread of the block when all columns pass.
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ int geweke_converged(double *gw, int CTm, int nwarps, int warp, int lane, TraceView tv, int m) {
+__host__ __device__ inline int dg_geweke_state_len(int CTm) { return 4 + 5 * CTm; }
+
+__device__ __noinline__ int geweke_converged(double *gw, double *gst, int CTm, int nwarps, int warp, int lane,
+                                             TraceView tv, int m) {
+    if (m <= 0) return 1;                                // empty series: Z is NaN, which is not > 2
     const int GC = CTm < DG_GW_COLS ? (CTm > 0 ? CTm : 1) : DG_GW_COLS;   // scratch columns per warp
     const int nA = (int)(0.1 * (double)m);
     const int iB = (int)(0.5 * (double)m);
     const int nB = m - iB;
+    const int nA0 = (int)gst[0];
+    int iB0 = (int)gst[1], mB0 = (int)gst[2];
+    const bool haveK = gst[3] != 0.0;
+    const bool resetB = iB >= mB0;                        // first check: window B starts empty at iB
+    if (resetB) { iB0 = iB; mB0 = iB; }
+    const int addA = nA - nA0, addB = m - mB0, subB = iB - iB0;
+    double *Kc = gst + 4, *SA = Kc + CTm, *QA = SA + CTm, *SB = QA + CTm, *QB = SB + CTm;
+    double *g0 = gw, *g1 = gw + nwarps * GC;
     int ok = 1;
     for (int c0 = 0; c0 < CTm; c0 += DG_GW_COLS) {
         const int col = c0 + lane;
         const bool act = col < CTm;
-        double *gA = gw, *gB = gw + nwarps * GC;
-        double sa = 0.0, sb = 0.0;
+        double K = 0.0;
+        if (act) K = haveK ? Kc[col] : __ldcg(tv.row(iB) + col);
+        // ---- window A: rows [nA0, nA) enter ----
+        double s = 0.0, q = 0.0;
         if (act) {
-            for (int r = warp; r < nA; r += nwarps) sa += __ldcg(tv.row(r) + col);
-            for (int r = iB + warp; r < m; r += nwarps) sb += __ldcg(tv.row(r) + col);
-        }
-        if (lane < GC) { gA[warp * GC + lane] = sa; gB[warp * GC + lane] = sb; }
-        __syncthreads();
-        double meanA = 0.0, meanB = 0.0;
-        if (lane < GC) {
-            for (int w = 0; w < nwarps; ++w) {
-                meanA += gA[w * GC + lane];
-                meanB += gB[w * GC + lane];
+            for (int i = warp; i < addA; i += nwarps) {
+                const double d = __ldcg(tv.row(nA0 + i) + col) - K;
+                s += d;
+                q = fma(d, d, q);
             }
         }
-        meanA /= (double)nA;
-        meanB /= (double)nB;
+        if (lane < GC) { g0[warp * GC + lane] = s; g1[warp * GC + lane] = q; }
         __syncthreads();
-        double qa = 0.0, qb = 0.0;
+        double sa = 0.0, qa = 0.0;
+        if (warp == 0 && act) {
+            if (nA0 > 0) { sa = SA[col]; qa = QA[col]; }
+            for (int w = 0; w < nwarps; ++w) { sa += g0[w * GC + lane]; qa += g1[w * GC + lane]; }
+        }
+        __syncthreads();
+        // ---- window B: rows [mB0, m) enter, rows [iB0, iB) leave ----
+        s = 0.0; q = 0.0;
         if (act) {
-            for (int r = warp; r < nA; r += nwarps) {
-                const double d = __ldcg(tv.row(r) + col) - meanA;
-                qa = fma(d, d, qa);
+            for (int i = warp; i < addB; i += nwarps) {
+                const double d = __ldcg(tv.row(mB0 + i) + col) - K;
+                s += d;
+                q = fma(d, d, q);
             }
-            for (int r = iB + warp; r < m; r += nwarps) {
-                const double d = __ldcg(tv.row(r) + col) - meanB;
-                qb = fma(d, d, qb);
+            for (int i = warp; i < subB; i += nwarps) {
+                const double d = __ldcg(tv.row(iB0 + i) + col) - K;
+                s -= d;
+                q = fma(-d, d, q);
             }
         }
-        if (lane < GC) { gA[warp * GC + lane] = qa; gB[warp * GC + lane] = qb; }
+        if (lane < GC) { g0[warp * GC + lane] = s; g1[warp * GC + lane] = q; }
         __syncthreads();
         if (warp == 0 && act) {
-            double va = 0.0, vb = 0.0;
-            for (int w = 0; w < nwarps; ++w) {
-                va += gA[w * GC + lane];
-                vb += gB[w * GC + lane];
-            }
-            va /= (double)nA;
-            vb /= (double)nB;
+            double sb = 0.0, qb = 0.0;
+            if (!resetB) { sb = SB[col]; qb = QB[col]; }
+            for (int w = 0; w < nwarps; ++w) { sb += g0[w * GC + lane]; qb += g1[w * GC + lane]; }
+            Kc[col] = K; SA[col] = sa; QA[col] = qa; SB[col] = sb; QB[col] = qb;
+            const double meanA = sa / (double)nA, meanB = sb / (double)nB;
+            double va = qa / (double)nA - meanA * meanA, vb = qb / (double)nB - meanB * meanB;
+            if (va < 0.0) va = 0.0;                       // rounding of an (almost) constant window
+            if (vb < 0.0) vb = 0.0;
             const double den = sqrt(va + vb);
             // reference: Z None (den == 0) or Z > 2 -> not converged; NaN compares false
             if (den == 0.0) ok = 0;
@@ -270,6 +298,7 @@ __device__ __noinline__ int geweke_converged(double *gw, int CTm, int nwarps, in
         }
         __syncthreads();
     }
+    if (threadIdx.x == 0) { gst[0] = (double)nA; gst[1] = (double)iB; gst[2] = (double)m; gst[3] = 1.0; }
     return __syncthreads_and(ok);
 }
 
@@ -366,15 +395,16 @@ __device__ __noinline__ long long trace_page(int64_t *ptab, int step, int pshift
 // ---------------------------------------------------------------------------------------
 // one chain, up to n_steps steps.  `slot` indexes the host stream blocks.
 // ---------------------------------------------------------------------------------------
-template <int KC, int WMODE, int D, bool CLUSTER>
+template <int KC, int WMODE, int J, bool CLUSTER>
 __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArgs &sa, int chain,
                           int slot, int n_steps, double *smem, int use_tma, int cs_rt, int crank_rt) {
     const int cs = CLUSTER ? cs_rt : 1, crank = CLUSTER ? crank_rt : 0;   // compile-time 1 / 0 for ordinary launches
-    constexpr int J = (1 << D) - 1;
-    constexpr int JP = J + 1;
+    constexpr int JP = (J + 1) & ~1;
+    constexpr int DT = J >= 4 ? 3 : (J >= 2 ? 2 : 1);     // levels of the speculation tree (J <= 7 nodes, heap order)
+    static_assert(J >= 1 && J <= 7, "1..7 candidate nodes per round");
     constexpr int SB = DG_STREAM_BLOCK;                   // stream steps produced per batch
-    constexpr int RING = 2 * SB;                          // ring of two batches
-    static_assert(SB >= 2 * D, "a stream batch must cover two rounds");
+    constexpr int RING = dg_ring_rows(J);                 // ring of 2-3 batches
+    static_assert(RING >= SB + 2 * J - 1, "the refilled batch must not overlap the rows of the next round");
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
 
@@ -389,7 +419,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     // shared memory once per round.  Only block 0 writes the trace and the chain status.
     const int SLOTS = cs > 1 ? DG_CLUSTER_SLOTS : DG_MAXWARPS;
     const bool lead = crank == 0;
-    const SmLayout L = dg_layout(C, Tc, nwarps, D, cs);
+    const SmLayout L = dg_layout(C, Tc, nwarps, J, cs);
     double *ycand = smem + L.ycand, *psic = smem + L.psic, *gs = smem + L.gs, *ex = smem + L.ex;
     double *pr = smem + L.pr, *ff = smem + L.ff, *zring = smem + L.zring, *dring = smem + L.dring;
     double *kinv = smem + L.kinv, *pfac = smem + L.pfac, *ijs = smem + L.ijs, *jcon = smem + L.jcon, *sqs = smem + L.sqs;
@@ -466,6 +496,8 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     int m = ct.m_next[chain];
     double *st = ct.st + ct.st_off[chain];
     const int rowlen = 2 * CT + 2;
+    double *gst = st + rowlen;                            // running Geweke sums (geweke_converged)
+    if (m == 0 && lead && tid < 4) gst[tid] = 0.0;
     int64_t *ptab = ct.ptab + ct.ptab_off[chain];
     const int pshift = ct.pshift[chain];
     const int pmask = (1 << pshift) - 1;
@@ -518,7 +550,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     // stream ring: two batches of SB steps; a new batch is produced (by the likelihood warps,
     // with all their lanes busy) whenever the chain is within one batch of the end of the ring
     int produced = m;                                     // ring holds steps [.., produced)
-    for (int b = 0; b < 2 && produced < m_end; ++b) {
+    for (int b = 0; b < RING / SB && produced < m_end; ++b) {
         const int upto = min(produced + SB, m_end);
         produce_stream(dev_stream, produced, upto, tid, nthreads, true, zring, dring, RING, C, Tc, pfac, sqs, kinv,
                        jcon, ijs, sa.seed, sid, dblk, ublk, m_start);
@@ -532,17 +564,20 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     for (int i = 0; i < 10; ++i) dg_prof[i] = 0;
 #endif
 
-    // Shape of the speculation tree for J = 3 candidates (uniform over the block, may change
-    // between rounds): 0 = full depth-2 tree {A, B|A rejected, B'|A accepted}: always 2 steps per
-    // round; 1 = rejection chain {A, B|A rej., C|A,B rej.}: 1 + (1-p) + (1-p)^2 steps per round,
-    // better when the acceptance rate p is below 0.38 (time-series genes run at ~0.16).
+    // Shape of the J candidate nodes of a round (uniform over the block, may change between
+    // rounds).  0 = binary tree in heap order (node 2j+1 follows a rejection of node j, 2j+2 an
+    // acceptance; J = 3: always 2 steps per round, J = 6: three levels without the accept-accept
+    // leaf).  1 = rejection chain: node d proposes step m+d from the unchanged state, the round
+    // ends at the first acceptance: (1 - (1-p)^J) / p steps per round, the better shape when the
+    // acceptance rate p is low (time-series genes run at ~0.16).
 #ifdef DG_NO_CHAIN
     constexpr bool kChain = false;
 #else
-    constexpr bool kChain = (J == 3);
+    constexpr bool kChain = (J >= 3);
 #endif
-    constexpr int DM = kChain ? 3 : D;                    // most steps a round can commit
-    int shape = (kChain && m > 0 && ct.cnt[chain] * 20 < m * 7) ? 1 : 0;
+    constexpr int kThr20 = (J == 3) ? 7 : 6;              // chain when p < kThr20 / 20
+    constexpr int DM = kChain ? J : DT;                   // most steps a round can commit
+    int shape = (kChain && m > 0 && ct.cnt[chain] * 20 < m * kThr20) ? 1 : 0;
     bool init = (m == 0);                                 // evaluate the start value first (model_GP.py:275-292)
     // next convergence-check step at or after m (m >= initial and m % gap == 0)
     int next_check = m > initial ? m : initial;
@@ -550,7 +585,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     int rbase = m % RING;                                 // ring slot of step m
     while (m < m_end || init) {
         // steps this round may commit: up to D, not past the chunk, not past a check step
-        const int nd_max = init ? 0 : min(shape ? DM : D, min(m_end - m, next_check - m + 1));
+        const int nd_max = init ? 0 : min(shape ? DM : DT, min(m_end - m, next_check - m + 1));
         // ================= S phase (state warps): candidates -> f =================
         double yj[J], bj[J], ej[J], gj[J];
         if (is_state) {
@@ -567,16 +602,19 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                         if (sl >= RING) sl -= RING;
                         dl[d] = d < nd_max ? dring[sl * RL + si] : 0.0;
                     }
-                    // node j (heap order): state before it proposes = Y_now moved through its accepted
-                    // ancestors; Y_try = delta + that state (:329, numpy adds the mean last)
+                    // state before node j proposes = Y_now moved through its accepted ancestors;
+                    // Y_try = delta + that state (:329, numpy adds the mean last)
+                    if (kChain && shape) {
 #pragma unroll
-                    for (int j = 0; j < J; ++j) {
-                        const int dep = (j >= 3) ? 2 : (j >= 1 ? 1 : 0);
-                        if (j == 0) bj[j] = y_now;
-                        else bj[j] = (j & 1) ? bj[(j - 1) / 2] : yj[(j - 1) / 2];   // odd = parent rejected
-                        double dj = dl[dep];
-                        if (kChain && j == 2 && shape) { bj[j] = y_now; dj = dl[DM - 1]; }   // chain: third proposal after two rejections
-                        yj[j] = dj + bj[j];
+                        for (int j = 0; j < J; ++j) { bj[j] = y_now; yj[j] = dl[j < DM ? j : 0] + y_now; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            const int dep = (j >= 3) ? 2 : (j >= 1 ? 1 : 0);
+                            if (j == 0) bj[j] = y_now;
+                            else bj[j] = (j & 1) ? bj[(j - 1) / 2] : yj[(j - 1) / 2];   // odd = parent rejected
+                            yj[j] = dl[dep] + bj[j];
+                        }
                     }
                 } else {
 #pragma unroll
@@ -762,6 +800,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                                     node = d + 1;
                                 } else {
                                     node = 2 * node + (acc ? 2 : 1);
+                                    if (node >= J) { nd_done = d + 1; break; }   // leaf not evaluated this round
                                 }
                             }
                             // a chain round that stopped early leaves the page cursor on its last
@@ -772,7 +811,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                             bc[6] = (nd_ok < nd_max) ? 1.0 : 0.0;            // trace pool exhausted
                             // shape of the next round from the running acceptance rate (p < 0.35 -> chain)
                             const int m_new = m + nd_done;
-                            bc[7] = (kChain && m_new >= 64 && cnt * 20 < m_new * 7) ? 1.0 : 0.0;
+                            bc[7] = (kChain && m_new >= 64 && cnt * 20 < m_new * kThr20) ? 1.0 : 0.0;
                         }
                     }
                 }
@@ -810,12 +849,12 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                 }
             }
             bar_state(nstate);                                               // candidates may be overwritten now
-        } else if (!init && produced < m_end && produced - (m + nd) <= SB) {
+        } else if (!init && produced < m_end && produced - (m + nd) <= RING - SB) {
             // the batch behind the chain is consumed: overwrite it with the next SB steps
             produce_stream(dev_stream, produced, min(produced + SB, m_end), tid - nstate, nthreads - nstate,
                            false, zring, dring, RING, C, Tc, pfac, sqs, kinv, jcon, ijs, sa.seed, sid, dblk, ublk, m_start);
         }
-        if (!init && produced < m_end && produced - (m + nd) <= SB) produced = min(produced + SB, m_end);
+        if (!init && produced < m_end && produced - (m + nd) <= RING - SB) produced = min(produced + SB, m_end);
         if (init) { init = false; continue; }
         shape = shape_next;
         m += nd;
@@ -832,7 +871,17 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         if (nd > 0 && mlast >= initial && (mlast % gap) == 0) {
             if (cs == 1) __syncthreads(); else cluster_barrier();        // the lead block's rows are visible
             DG_TICK(4);
-            const int conv = geweke_converged(gw, CTm, nwarps, warp, lane, tv, mlast);
+            int conv;
+            if (cs == 1) {
+                conv = geweke_converged(gw, gst, CTm, nwarps, warp, lane, tv, mlast);
+            } else {                                                     // the lead block decides for the cluster
+                if (lead) {
+                    conv = geweke_converged(gw, gst, CTm, nwarps, warp, lane, tv, mlast);
+                    if (tid == 0) for (int r = 0; r < cs; ++r) st_cluster(bc + 8, r, (double)conv);
+                }
+                cluster_barrier();
+                conv = (int)bc[8];
+            }
             DG_TICK(5);
             if (conv) {
                 state = DICEGP_CHAIN_CONVERGED_;

@@ -97,12 +97,19 @@ struct SmLayout {
     int total;                                                 // doubles without W
 };
 
-__host__ __device__ inline SmLayout dg_layout(int C, int Tc, int nwarps, int D, int cs = 1) {
+// rows of the stream ring for rounds that commit up to J steps: a batch of DG_STREAM_BLOCK steps
+// is refilled while the next round already reads its own (up to J) rows
+__host__ __device__ constexpr int dg_ring_rows(int J) {
+    return ((DG_STREAM_BLOCK + 2 * J - 1 + DG_STREAM_BLOCK - 1) / DG_STREAM_BLOCK) * DG_STREAM_BLOCK;
+}
+
+// J = candidate nodes evaluated per round (per pass over W)
+__host__ __device__ inline SmLayout dg_layout(int C, int Tc, int nwarps, int J, int cs = 1) {
     SmLayout L;
     // partial-likelihood slots: one per likelihood warp of the chain; a cluster of cs blocks
     // shares them (DG_CLUSTER_SLOTS) and double-buffers them across rounds
     const int GWS = cs > 1 ? DG_CLUSTER_SLOTS : DG_MAXWARPS, NBUF = cs > 1 ? 2 : 1;
-    const int J = (1 << D) - 1, JP = J + 1, RING = 2 * DG_STREAM_BLOCK;
+    const int JP = (J + 1) & ~1, RING = dg_ring_rows(J);
     int CT = C * Tc, TT = Tc * Tc, o = 0;
     L.ycand = o; o += J * CT;  L.psic = o; o += J * CT;  L.gs = o; o += J * CT;  L.ex = o; o += J * CT;
     L.pr = o; o += J * CT;
