@@ -471,7 +471,7 @@ inline int kind_of(int C) { return (C >= 2 && C <= 8) ? C - 1 : 0; }
 // likelihood warp
 inline int min_threads(int C, int Tc) { return ((C * Tc + 31) / 32) * 32 + 32; }
 
-int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain) {
+int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain, int latency_mode) {
     const dicegp_chain_desc &d = c->hdesc[chain];
     const int C = c->hC[d.gene];
     const int64_t wb = chain_wbytes(c, chain);
@@ -480,7 +480,13 @@ int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain) {
     if (wb >= 16 * wide_min) return 7;
     if (wb >= 4 * wide_min) return 6;
     if (wb >= wide_min) return 5;
-    for (int i = 0; i < 4; ++i) {
+    // A resident chain that needs a whole SM leaves it idle during the serial part of every round;
+    // four streamed chains per SM overlap each other's serial parts and are faster (measured:
+    // 23.5 vs 29.7 ms for 592 two-isoform, 128 KB chains), so the one-block-per-SM resident class
+    // is only taken in latency mode (one chain per SM anyway).
+    static const int max_resident_env = getenv("DICEGP_MAX_RESIDENT_TIER") ? atoi(getenv("DICEGP_MAX_RESIDENT_TIER")) : -1;
+    const int max_resident = max_resident_env >= 0 ? max_resident_env : (latency_mode ? 3 : 2);
+    for (int i = 0; i <= max_resident && i < 4; ++i) {
         if (cls[i].threads < min_threads(C, d.Tc)) continue;
         if (fixed_smem_bytes(C, d.Tc, cls[i].threads, false) + (size_t)wb <= cls[i].smem_limit) return i;
     }
@@ -562,7 +568,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     for (size_t i = 0; i < ids.size(); ++i) {
         const dicegp_chain_desc &d = c->hdesc[ids[i]];
         const int C = c->hC[d.gene];
-        int tier = pick_tier(c, cls, ids[i]);
+        int tier = pick_tier(c, cls, ids[i], latency_mode);
         if (latency_mode == 2 && tier == 4) tier = 6;          // last stragglers: a cluster of 4 blocks each
         const int k = tier * kKinds + kind_of(C);
         by_group[k].push_back(ids[i]);
