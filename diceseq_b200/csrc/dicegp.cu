@@ -648,7 +648,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             if (tier == 4 && !getenv("DICEGP_TIER_THREADS")) {
                 int best_score = -1;
                 for (int kk = 1; kk <= (latency_mode ? 1 : 4); ++kk) {
-                    for (int nwl = 2; nwl <= 14; ++nwl) {
+                    for (int nwl = 2; nwl <= DG_LB_THREADS / 32 - 2; ++nwl) {
                         const int thr = 32 * (maxS + nwl);
                         if (thr * kk > DG_LB_THREADS) continue;
                         size_t need = fixed_smem_bytes(maxC, maxTc, thr, true) + 1024;
@@ -665,7 +665,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             if (tier >= 5) {
                 // cluster tier: as many likelihood warps per block as the staging ring allows
                 int best = -1;
-                for (int nwl = 2; nwl <= 14; ++nwl) {
+                for (int nwl = 2; nwl <= DG_LB_THREADS / 32 - 2; ++nwl) {
                     const int thr = 32 * (maxS + nwl);
                     if (thr > DG_LB_THREADS) break;
                     size_t need = fixed_smem_bytes(maxC, maxTc, thr, true, cs) + 1024;

@@ -68,7 +68,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Likelihood pass of one warp.  The chain's reads are cut into ITEMS of 32 consecutive read
-// pairs of one time point (cum[t] = first item of time t); item q belongs to warp q % NWL.
+// pairs of one time point (cum[t] = first item of time t); warp wl of NWL takes a contiguous
+// run of items, so it changes time point (and reloads f) only a few times per pass.
 //   x_n^(j) = sum_k W[n,k] f^(j)[k]                            model_GP.py:338
 // W block of a time point: isoform-major, row k = npairs double2 (two reads per 16-byte
 // word; consecutive lanes take consecutive words: conflict-free LDS.128 / coalesced
@@ -83,19 +84,27 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
     constexpr int JP = (J + 1) & ~1;
     const int nitems = cum[Tc];
     const int kmax = KC > 0 ? KC : C;
+    const int per = (nitems + NWL - 1) / NWL;
+    const int q0 = min(wl * per, nitems), q1 = min(q0 + per, nitems);
+    if (q0 >= q1) return;
     double2 *mystage = reinterpret_cast<double2 *>(stage) + lane;     // [stage][k][32 lanes]
-    int qi = wl, tti = 0;                                             // issue cursor (W_STAGED)
+    // issue cursor (W_STAGED): item qi of time point ti, lane's pair ip of inp, source word isrc
+    int qi = q0, ti = 0, ip = 0, inp = 0;
+    const double2 *isrc = nullptr;
     auto issue = [&](int slot) {
-        if (qi < nitems) {
-            while (qi >= cum[tti + 1]) ++tti;
-            const int r0 = rel[tti], npairs = (rel[tti + 1] - r0) >> 1;
-            const int p = (qi - cum[tti]) * 32 + lane;
-            if (p < npairs) {
-                const double2 *src = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0) + p;
-#pragma unroll
-                for (int k = 0; k < kmax; ++k) cp_async16(mystage + (slot * kmax + k) * 32, src + (size_t)k * npairs);
+        if (qi < q1) {
+            if (isrc == nullptr || qi >= cum[ti + 1]) {
+                while (qi >= cum[ti + 1]) ++ti;
+                const int r0 = rel[ti];
+                inp = (rel[ti + 1] - r0) >> 1;
+                ip = (qi - cum[ti]) * 32 + lane;
+                isrc = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0) + ip;
             }
-            qi += NWL;
+            if (ip < inp) {
+#pragma unroll
+                for (int k = 0; k < kmax; ++k) cp_async16(mystage + (slot * kmax + k) * 32, isrc + (size_t)k * inp);
+            }
+            ++qi; ip += 32; isrc += 32;
         }
         cp_async_commit();
     };
@@ -103,14 +112,15 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
 #pragma unroll
         for (int s = 0; s < kStages - 1; ++s) issue(s);
     }
-    constexpr bool FREG = (KC > 0 && KC * J <= (J > 3 ? 18 : 24));                  // f of the time point held in registers
+    constexpr bool FREG = (KC > 0 && KC * J <= (J > 3 ? 18 : 24));    // f of the time point held in registers
     constexpr int FR = FREG ? KC : 1;
-    int it = 0, q = wl;
-    for (int tt = 0; tt < Tc; ++tt) {
-        const int c0 = cum[tt], c1 = cum[tt + 1];
-        if (q >= c1) continue;
+    int it = 0, q = q0, tt = 0;
+    while (q < q1) {
+        while (q >= cum[tt + 1]) ++tt;
+        const int c0 = cum[tt], c1 = min(cum[tt + 1], q1);
         const int r0 = rel[tt], npairs = (rel[tt + 1] - r0) >> 1, n = ncnt[tt];
-        const double2 *Wt0 = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0) + lane;
+        int p = (q - c0) * 32 + lane;
+        const double2 *Wt = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0) + p;
         const double *ffcol = ff + (size_t)tt * C * JP;
         double fr[FR][J];
         if (FREG) {
@@ -121,14 +131,12 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
             }
         }
 #pragma unroll((WMODE == W_STAGED && J <= 3) ? 2 : 1)
-        for (; q < c1; q += NWL, ++it) {
-            const int p = (q - c0) * 32 + lane;
+        for (; q < c1; ++q, ++it, p += 32, Wt += 32) {
             if (WMODE == W_STAGED) {
                 issue((it + kStages - 1) & (kStages - 1));
                 cp_async_wait<kStages - 1>();
             }
             if (p < npairs) {
-                const double2 *Wt = Wt0 + (q - c0) * 32;
                 const double2 *st = mystage + ((it & (kStages - 1)) * kmax) * 32;
                 double x0[J], x1[J];
 #pragma unroll
@@ -164,11 +172,17 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
                 } else {
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
+                        // the two reads of the pair are multiplied first: scaling by powers of two is
+                        // exact, so mant(x0 * x1) carries the same bits as mant(x0) * mant(x1); a
+                        // product that leaves the positive normal range (a zero, negative or
+                        // non-finite x, or an under/overflow) sends the round to the log path
                         const double y1 = v1 ? x1[j] : 1.0;
-                        const int h0 = __double2hiint(x0[j]), h1 = __double2hiint(y1);
-                        bad |= (((unsigned)(h0 - 0x00100000) >= 0x7fe00000u) || ((unsigned)(h1 - 0x00100000) >= 0x7fe00000u)) ? 1u : 0u;
-                        ee[j] += (h0 >> 20) + (h1 >> 20) - 2046;
-                        mm[j] *= dg_mant(x0[j], h0) * dg_mant(y1, h1);
+                        const double pr2 = x0[j] * y1;
+                        const int h = __double2hiint(pr2);
+                        bad |= ((unsigned)(h - 0x00100000) >= 0x7fe00000u) ? 1u : 0u;
+                        bad |= (unsigned)(__double2hiint(x0[j]) | __double2hiint(y1)) >> 31;   // two negative x would hide each other
+                        ee[j] += (h >> 20) - 1023;
+                        mm[j] *= dg_mant(pr2, h);
                     }
                 }
             }
