@@ -187,51 +187,77 @@ __global__ void dicegp_gather_rows_kernel(ChainTab ct, int chain, int rowlen, in
 //   shared memory; lik_marg = log n + min - log(sum exp(min - Lik)).
 // ---------------------------------------------------------------------------------------
 #define DG_SUM_THREADS 256
-__device__ unsigned long long dg_radix_select(const unsigned long long *keys, int n, int rank,
-                                              unsigned *hist, int *sh) {
-    // rank-th smallest (0-based) of n keys; hist: 256 bins; sh: 2 ints
-    unsigned long long prefix = 0, mask = 0;
+// Two order statistics of the same n keys in one sweep: rank[0]-th and rank[1]-th smallest
+// (0-based), by 8-bit radix selection from the top digit down.  Both selections share every
+// pass over the keys (two histograms); the histogram updates are aggregated per warp, because
+// the keys of a trace column share their sign / exponent digits and would otherwise all hit
+// the same bin.  hist: 2 x 256 bins; sh: 4 ints.  Block-wide; every thread gets both results.
+__device__ void dg_radix_select2(const unsigned long long *keys, int n, int rank0, int rank1, unsigned *hist, int *sh,
+                                 unsigned long long &out0, unsigned long long &out1) {
+    unsigned long long prefix[2] = {0, 0}, mask = 0;
+    int rank[2] = {rank0, rank1};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_up = (n + 31) & ~31;                      // whole warps stay in the loop (match needs them)
     for (int shift = 56; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const unsigned long long k = keys[i];
-            if ((k & mask) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+        const bool same = prefix[0] == prefix[1];         // both selections still walk the same bucket
+        for (int i = threadIdx.x; i < n_up; i += blockDim.x) {
+            const bool ok = i < n;
+            const unsigned long long k = ok ? keys[i] : 0ull;
+            const unsigned d = (unsigned)(k >> shift) & 255u;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s == 1 && same) break;
+                const bool in = ok && (k & mask) == prefix[s];
+                if (shift >= 48) {                        // sign / exponent digits: a handful of distinct values
+                    const unsigned peers = __match_any_sync(0xffffffffu, in ? d : 256u + (unsigned)lane);
+                    if (in && lane == __ffs(peers) - 1) atomicAdd(&hist[s * 256 + d], (unsigned)__popc(peers));
+                } else if (in) {
+                    atomicAdd(&hist[s * 256 + d], 1u);
+                }
+            }
         }
         __syncthreads();
-        if (threadIdx.x < 32) {
-            // warp scan over 256 bins: 8 bins per lane
+        if (warp < 2) {
+            // warp s scans the 256 bins of selection s: 8 bins per lane
+            const unsigned *h = hist + (same ? 0 : warp * 256);
             unsigned loc[8], tot = 0;
-            for (int j = 0; j < 8; ++j) { loc[j] = hist[threadIdx.x * 8 + j]; tot += loc[j]; }
+            for (int j = 0; j < 8; ++j) { loc[j] = h[lane * 8 + j]; tot += loc[j]; }
             unsigned incl = tot;
             for (int off = 1; off < 32; off <<= 1) {
                 unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
-                if ((int)threadIdx.x >= off) incl += v;
+                if (lane >= off) incl += v;
             }
-            unsigned before = incl - tot;
-            if ((unsigned)rank >= before && (unsigned)rank < incl) {
+            const unsigned before = incl - tot;
+            const unsigned r = (unsigned)rank[warp];
+            if (r >= before && r < incl) {
                 unsigned acc = before;
                 for (int j = 0; j < 8; ++j) {
-                    if ((unsigned)rank < acc + loc[j]) { sh[0] = threadIdx.x * 8 + j; sh[1] = rank - (int)acc; break; }
+                    if (r < acc + loc[j]) { sh[2 * warp] = lane * 8 + j; sh[2 * warp + 1] = (int)(r - acc); break; }
                     acc += loc[j];
                 }
             }
         }
         __syncthreads();
-        prefix |= (unsigned long long)(unsigned)sh[0] << shift;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            prefix[s] |= (unsigned long long)(unsigned)sh[2 * s] << shift;
+            rank[s] = sh[2 * s + 1];
+        }
         mask |= 0xffull << shift;
-        rank = sh[1];
         __syncthreads();
     }
-    return prefix;
+    out0 = prefix[0];
+    out1 = prefix[1];
 }
 
 __global__ void __launch_bounds__(DG_SUM_THREADS)
 dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, double *__restrict__ mean_out,
                       double *__restrict__ ci_out, const int64_t *__restrict__ out_off, double *__restrict__ lik_out) {
     extern __shared__ __align__(16) unsigned long long dg_keys[];
-    __shared__ unsigned hist[256];
-    __shared__ int sh[2];
+    __shared__ unsigned hist[512];
+    __shared__ int sh[4];
     __shared__ double red[DG_SUM_THREADS / 32];
     const int chain = ids[blockIdx.x];
     const int C = gt.C[ct.gene[chain]], Tc = ct.Tc[chain], CT = C * Tc, rowlen = 2 * CT + 2;
@@ -269,8 +295,8 @@ dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, 
         for (int i = tid; i < n; i += blockDim.x)
             dg_keys[i] = (unsigned long long)__double_as_longlong(__ldcg(tv.row(b + i) + col));
         __syncthreads();
-        const unsigned long long lo = dg_radix_select(dg_keys, n, k, hist, sh);
-        const unsigned long long hi = dg_radix_select(dg_keys, n, k > 0 ? n - k : 0, hist, sh);
+        unsigned long long lo, hi;
+        dg_radix_select2(dg_keys, n, k, k > 0 ? n - k : 0, hist, sh, lo, hi);
         if (tid == 0) {
             ci[2 * col] = __longlong_as_double((long long)hi);       // sorted[-k]
             ci[2 * col + 1] = __longlong_as_double((long long)lo);   // sorted[k]
@@ -1234,7 +1260,7 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
         total = std::max<int64_t>(total, out_off[i] + (int64_t)c->hC[d.gene] * d.Tc);
         smem = std::max(smem, (size_t)d.M * sizeof(unsigned long long));
     }
-    if (smem > c->smem_optin - 2048) return c->fail(DICEGP_ERR_LIMIT, "posterior_summary: M too large for the shared-memory radix select");
+    if (smem > c->smem_optin - 4096) return c->fail(DICEGP_ERR_LIMIT, "posterior_summary: M too large for the shared-memory radix select");
     // Launch groups by rows kept: the radix select holds one column in shared memory, so
     // short chains (the bulk) run 8 blocks per SM and only the long ones need a whole SM.
     std::vector<int32_t> ids(chain_ids, chain_ids + n), nr(n);
@@ -1268,7 +1294,7 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
     do {
         if ((e = cudaMemcpyAsync(doff.p, off_sorted.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(dids.p, ids_sorted.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
-        if ((e = cudaFuncSetAttribute(dicegp_summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - 2048))) != cudaSuccess) break;
+        if ((e = cudaFuncSetAttribute(dicegp_summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - 4096))) != cudaSuccess) break;
         for (int k = 0; k < 4 && e == cudaSuccess; ++k) {
             const int cnt = gstart[k + 1] - gstart[k];
             if (cnt == 0) continue;
