@@ -160,13 +160,18 @@ class BatchSampler:
             theta2 = ((np.max(X) - np.min(X) + 0.1) / 3.0) ** 2       # diceseq.py:169
         gene_ids = np.arange(G, dtype=np.int64) if gene_ids is None else np.asarray(gene_ids, dtype=np.int64)
         self.stats = {}
+        wall = {}                                         # host wall time of each stage (ms)
 
         # 1. pre-runs (run_utils.py:107-115)
+        _t = _time.perf_counter()
         ctx.set_prerun_chains(theta1, 0.1, 100, 100, 50)
+        wall["set_prerun"] = (_time.perf_counter() - _t) * 1e3
         if stream == "device":
+            _t = _time.perf_counter()
             sid = (gene_ids[:, None] * (T + 1) + np.arange(T)[None, :]).ravel()
             ctx.run_device_stream(seed, sid)
             self._acc_stats("prerun")
+            wall["run_prerun"] = (_time.perf_counter() - _t) * 1e3
         else:
             rng = np.random.Generator(np.random.Philox(key=seed))
             js_rows = []
@@ -183,18 +188,24 @@ class BatchSampler:
         kinv = np.linalg.inv(K)
         prior_const = -(T * _LOG_2PI + np.log(det)) / 2.0
         pf = proposal_factor(K)
+        _t = _time.perf_counter()
         var = ctx.main_chains_from_prerun(M, initial, gap, theta1, kinv, pf, prior_const)
+        wall["set_main"] = (_time.perf_counter() - _t) * 1e3
 
         # 3. main run (run_utils.py:120-122)
         if stream == "device":
+            _t = _time.perf_counter()
             ctx.run_device_stream(seed, gene_ids * (T + 1) + T)
             self._acc_stats("main")
+            wall["run_main"] = (_time.perf_counter() - _t) * 1e3
         else:
             js_rows = [var[g, :int(packed.n_iso[g]) - 1] * 5 / (T * int(packed.n_iso[g]) * theta1) for g in range(G)]
             self._run_host(rng, js_rows, pf, T, initial, gap)
 
         # 4. results: burn-in summaries are reduced on the device (run_utils.py:125-129)
+        _t = _time.perf_counter()
         st = ctx.chain_status()
+        wall["status"] = (_time.perf_counter() - _t) * 1e3
         if (st["state"] == _lib.CHAIN_NOMEM).any():
             raise MemoryError("%d chains ran out of trace memory; raise Context.set_trace_budget or "
                               "use smaller batches" % int((st["state"] == _lib.CHAIN_NOMEM).sum()))
@@ -206,8 +217,63 @@ class BatchSampler:
         if keep_trace:
             res.traces = [ctx.download_trace(g, int(st["n_rows"][g])) for g in range(G)]
         self.stats["sample_ms"] = (_time.perf_counter() - _t0) * 1e3
+        self.stats["wall_ms"] = wall
         return res
 
     def run(self, packed, **kw):
         self.upload(packed)
         return self.sample(**kw)
+
+
+class PipelinedSampler:
+    """A stream of gene batches on one GPU with the host->device copy of batch k+1 hidden behind
+    the sampling of batch k: two `BatchSampler`s (two C-ABI contexts, each with its own device
+    buffers and streams) alternate; the copy of the next batch is issued from a helper thread on
+    the idle context's stream while the busy one runs its kernels (the copy engine and the SMs
+    work concurrently; ctypes drops the GIL inside the library).  Results are identical to
+    running the batches one after another through a single `BatchSampler`."""
+
+    def __init__(self, device=0, trace_budget_bytes=0):
+        self.samplers = [BatchSampler(device), BatchSampler(device)]
+        if trace_budget_bytes:
+            for s in self.samplers:
+                s.ctx.set_trace_budget(int(trace_budget_bytes))
+
+    def close(self):
+        for s in self.samplers:
+            s.close()
+
+    def run_stream(self, batches):
+        """batches: iterable of (PackedGenes, sample-kwargs).  Yields (BatchResult, stats) in order."""
+        import threading
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        self.samplers[0].upload(cur[0])
+        k = 0
+        while cur is not None:
+            nxt = next(it, None)
+            th, err = None, []
+            if nxt is not None:
+                def _up(s=self.samplers[(k + 1) % 2], packed=nxt[0]):
+                    try:
+                        import time as _time
+                        _t = _time.perf_counter()
+                        s.upload(packed)
+                        self.last_upload_ms = (_time.perf_counter() - _t) * 1e3
+                    except BaseException as e:          # re-raised in the caller's thread below
+                        err.append(e)
+                th = threading.Thread(target=_up)
+                th.start()
+            s = self.samplers[k % 2]
+            try:
+                res = s.sample(**cur[1])
+            finally:
+                if th is not None:
+                    th.join()
+            if err:
+                raise err[0]
+            yield res, dict(s.stats)
+            cur = nxt
+            k += 1

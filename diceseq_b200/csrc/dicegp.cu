@@ -938,7 +938,14 @@ int dicegp_upload_genes(dicegp_ctx *c, int32_t G, int32_t T, const int32_t *n_is
     DG_CUDA(c, cudaMemcpyAsync(c->droff.p, c->hroff.data(), (size_t)G * (T + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     DG_CUDA(c, cudaMemcpyAsync(c->dwoff.p, c->hwoff.data(), G * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     DG_CUDA(c, cudaMemcpyAsync(c->dlenoff.p, c->hlenoff.data(), G * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-    if (w > 0) DG_CUDA(c, cudaMemcpyAsync(c->dW.p, W, w * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // W goes up in 16 MB pieces, each submitted when the previous one has landed: another context
+    // sampling on this GPU at the same time (PipelinedSampler) issues many small host->device copies,
+    // which would otherwise queue behind one multi-GB transfer on the copy engine
+    for (int64_t o = 0; o < w; o += (2 << 20)) {
+        const int64_t cnt = std::min<int64_t>(w - o, 2 << 20);
+        DG_CUDA(c, cudaMemcpyAsync(c->dW.p + o, W + o, cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        DG_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     DG_CUDA(c, cudaMemcpyAsync(c->dlen.p, len_iso, l * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     DG_CUDA(c, cudaStreamSynchronize(c->stream));
     c->h2d_bytes += (w + l) * (int64_t)sizeof(double) + ((int64_t)G * (2 * T + 2) ) * 4 + (int64_t)G * 16;

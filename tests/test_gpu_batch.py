@@ -141,3 +141,21 @@ def test_trace_pool_grows_and_reports_exhaustion():
             s.run(packed, M=5000, initial=4000, gap=500, seed=1, gene_ids=genes)
     finally:
         s.close()
+
+
+def test_pipelined_stream_equals_one_batch_at_a_time():
+    """PipelinedSampler (copy of batch k+1 hidden behind the sampling of batch k, two contexts)
+    returns bit-identical results to a single BatchSampler fed the same batches in turn."""
+    from diceseq_b200.batch import PipelinedSampler
+    batches = [(_batch("timeseries", list(range(60 + 6 * b, 66 + 6 * b))), dict(M=2000, seed=b, gene_ids=np.arange(6) + 6 * b))
+               for b in range(3)]
+    pipe = PipelinedSampler(0)
+    got = [r for r, _st in pipe.run_stream(iter(batches))]
+    pipe.close()
+    one = BatchSampler(0)
+    for (packed, kw), r in zip(batches, got):
+        ref = one.run(packed, **kw)
+        assert np.array_equal(ref.m, r.m) and np.array_equal(ref.cnt, r.cnt)
+        assert np.array_equal(ref.psi_mean, r.psi_mean) and np.array_equal(ref.psi_ci, r.psi_ci)
+        assert np.array_equal(ref.lik_marg, r.lik_marg)
+    one.close()
