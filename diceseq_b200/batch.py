@@ -235,9 +235,15 @@ class PipelinedSampler:
 
     def __init__(self, device=0, trace_budget_bytes=0):
         self.samplers = [BatchSampler(device), BatchSampler(device)]
-        if trace_budget_bytes:
-            for s in self.samplers:
-                s.ctx.set_trace_budget(int(trace_budget_bytes))
+        self.current = None
+        self.last_upload_ms = 0.0
+        if not trace_budget_bytes:
+            # a context sizes its trace pool from the memory that is free when its chains are
+            # installed; two contexts share the GPU, so each gets a fixed 30 % of what is free now
+            import torch
+            trace_budget_bytes = int(0.3 * torch.cuda.mem_get_info(device)[0])
+        for s in self.samplers:
+            s.ctx.set_trace_budget(int(trace_budget_bytes))
 
     def close(self):
         for s in self.samplers:
@@ -267,6 +273,7 @@ class PipelinedSampler:
                 th = threading.Thread(target=_up)
                 th.start()
             s = self.samplers[k % 2]
+            self.current = s                              # the context that holds this batch's traces
             try:
                 res = s.sample(**cur[1])
             finally:

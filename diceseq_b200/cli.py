@@ -129,21 +129,38 @@ def main(argv=None):
             inputs = pool.map(_inputs_worker, jobs, chunksize=max(1, len(jobs) // (8 * options.nproc)))
 
     # ---- stage 2: GPU sampling of the multi-isoform genes -----------------------------------
-    from .batch import BatchSampler
+    from .batch import BatchSampler, PipelinedSampler
     from .packer import clean_inputs, pack_genes
     multi = [i for i, g in enumerate(genes) if g.tranNum > 1]
     results = {}
     samples = {}
-    sampler = BatchSampler(options.device) if multi else None
-    for b0 in range(0, len(multi), options.batch):
-        idx = multi[b0:b0 + options.batch]
-        packed_in = []
-        for i in idx:
-            R_all, len_all, prob_all, _count = inputs[i]
-            clean_inputs(R_all, len_all, prob_all)                   # model_GP.py:250-264
-            packed_in.append(([R * P for R, P in zip(R_all, prob_all)], len_all))
-        res = sampler.run(pack_genes(packed_in), X=X, theta1=theta1, theta2=theta2, M=Mmax, initial=Mmin,
-                          gap=Mgap, seed=options.seed, gene_ids=np.array(idx))
+    chunks = [multi[b0:b0 + options.batch] for b0 in range(0, len(multi), options.batch)]
+
+    def batches():
+        for idx in chunks:
+            packed_in = []
+            for i in idx:
+                R_all, len_all, prob_all, _count = inputs[i]
+                clean_inputs(R_all, len_all, prob_all)               # model_GP.py:250-264
+                packed_in.append(([R * P for R, P in zip(R_all, prob_all)], len_all))
+            yield pack_genes(packed_in, pinned=len(chunks) > 1), dict(
+                X=X, theta1=theta1, theta2=theta2, M=Mmax, initial=Mmin, gap=Mgap, seed=options.seed,
+                gene_ids=np.array(idx))
+
+    # several batches: the copy of batch k+1 overlaps the sampling of batch k (two contexts)
+    pipe = (PipelinedSampler(options.device) if len(chunks) > 1 else None)
+    single = BatchSampler(options.device) if len(chunks) == 1 else None
+
+    def run_all():
+        if pipe is not None:
+            for res, _st in pipe.run_stream(batches()):
+                yield res, pipe.current
+        elif single is not None:
+            for packed, kw in batches():
+                yield single.run(packed, **kw), single
+
+    done = 0
+    for (res, sampler), idx in zip(run_all(), chunks):
         for k, i in enumerate(idx):
             results[i] = res[k]
             if sample_num > 0:
@@ -154,11 +171,12 @@ def main(argv=None):
                     samples[i] = Y
                 else:
                     samples[i] = np.zeros((0, genes[i].tranNum, T))
-        sys.stdout.write("\r[DICEseq] %d / %d genes sampled in %.1f sec." % (min(b0 + options.batch, len(multi)),
-                                                                             len(multi), time.time() - start_time))
+        done += len(idx)
+        sys.stdout.write("\r[DICEseq] %d / %d genes sampled in %.1f sec." % (done, len(multi), time.time() - start_time))
         sys.stdout.flush()
-    if sampler is not None:
-        sampler.close()
+    for s_ in (pipe, single):
+        if s_ is not None:
+            s_.close()
 
     # ---- stage 3: output, in annotation order -----------------------------------------------
     out_dir = os.path.dirname(options.out_file)
