@@ -112,7 +112,10 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
 #pragma unroll
         for (int s = 0; s < kStages - 1; ++s) issue(s);
     }
-    constexpr bool FREG = (KC > 0 && KC * J <= (J > 3 ? 18 : 24));    // f of the time point held in registers
+#ifndef DG_FREG_MAX
+#define DG_FREG_MAX 12
+#endif
+    constexpr bool FREG = (KC > 0 && KC * J <= (J > 3 ? 18 : DG_FREG_MAX));    // f of the time point held in registers
     constexpr int FR = FREG ? KC : 1;
     int it = 0, q = q0, tt = 0;
     while (q < q1) {
