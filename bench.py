@@ -310,6 +310,14 @@ def run_ours(args, wl):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (main_ms * 1e-3) / 1e9 if main_ms > 0 else 0.0
+    # DRAM bytes of the main-run launch set of ONE step, from the committed ncu launch list of this
+    # command (dram__bytes_read.sum + dram__bytes_write.sum); only valid for the profiled configuration
+    traffic = None
+    try:
+        if args.workload == "timeseries" and G == WORKLOADS["timeseries"]["genes"]:
+            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))["main_run_dram_bytes_per_step"])
+    except (OSError, KeyError, ValueError):
+        traffic = None
 
     line = {
         "metric": "read_likelihood_evals_per_s", "value": total_evals / (resident_ms * 1e-3), "unit": "evals/s",
@@ -326,7 +334,9 @@ def run_ours(args, wl):
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "traffic_unit": "bytes per step (main-run launch set, profiles/traffic_r01.json)",
+                     "algorithmic_bytes_per_step": alg_bytes / args.steps,
                      "kernel": "dicegp_chain_kernel (main-run launch set: one launch per residency class, concurrent)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "note": "algorithmic bytes = sum over main-run MH steps of 8*C*N + stream + trace row; W is "
