@@ -678,7 +678,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                         const int thr = 32 * (maxS + nwl);
                         if (thr * kk > DG_LB_THREADS) continue;
                         size_t need = fixed_smem_bytes(maxC, maxTc, thr, true) + 1024;
-                        if (kind != 0) need += (size_t)nwl * dg::kStages * maxC * 512;
+                        if (kind != 0) need += (size_t)nwl * dg::dg_stages(maxC) * dg::dg_stage_slot_bytes(maxC);
                         if (need * kk > 233472) continue;
                         // at least 8 streaming warps per SM, then as many chains as possible (their serial
                         // phases overlap), then more warps
@@ -695,7 +695,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                     const int thr = 32 * (maxS + nwl);
                     if (thr > DG_LB_THREADS) break;
                     size_t need = fixed_smem_bytes(maxC, maxTc, thr, true, cs) + 1024;
-                    if (kind != 0) need += (size_t)nwl * dg::kStages * maxC * 512;
+                    if (kind != 0) need += (size_t)nwl * dg::dg_stages(maxC) * dg::dg_stage_slot_bytes(maxC);
                     if (need > 233472) break;
                     best = thr;
                 }
@@ -714,7 +714,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                     // per likelihood warp: kStages x C x 32 lanes x 16 bytes of cp.async staging
                     const int C = c->hC[d.gene];
                     const int nwl = threads / 32 - (C * d.Tc + 31) / 32;
-                    need += (size_t)nwl * dg::kStages * C * 512;
+                    need += (size_t)nwl * dg::dg_stages(C) * dg::dg_stage_slot_bytes(C);
                 }
                 smem = std::max(smem, need);
             }

@@ -26,6 +26,9 @@
 
 namespace dg {
 
+// named barriers: 0 = the whole block, 2 = state warps, 3 = likelihood warps
+__device__ __forceinline__ void dg_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void dg_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_state(int n) { asm volatile("bar.sync 2, %0;" ::"r"(n) : "memory"); }
 __device__ __forceinline__ void bar_lik(int n) { asm volatile("bar.sync 3, %0;" ::"r"(n) : "memory"); }
 
@@ -58,7 +61,31 @@ __device__ __forceinline__ double dg_mant(double x, int hi) {
 //               copies exactly the 16-byte words it will consume: no barrier, deep prefetch)
 //   W_DIRECT    plain global loads (isoform counts too large for the staging ring)
 enum { W_RESIDENT = 0, W_STAGED = 1, W_DIRECT = 2 };
-constexpr int kStages = 4;
+// Shape of a likelihood item, per isoform count C:
+//   words   16-byte words (read pairs) a lane handles per item.  The words of a lane are independent
+//           dependency chains in one basic block, which the scheduler interleaves (a likelihood
+//           warp is bound by instruction latency, not by a throughput limit), and their reads
+//           share one exponent extraction.
+//   stages  depth of the per-warp cp.async ring of the streamed tiers (stages-1 items in flight);
+//           any depth >= 2 (ring slots are counted, not masked).
+// Measured on 592-chain groups of the bench workload (scripts/stream_sweep.py); DG_ITEM_WORDS /
+// DG_STAGE_BYTES / DG_MIN_STAGES override the table for experiments.
+__host__ __device__ constexpr int dg_item_words(int C) {
+#ifdef DG_ITEM_WORDS
+    return DG_ITEM_WORDS;
+#else
+    return C <= 2 ? 4 : (C <= 8 ? 2 : 1);
+#endif
+}
+__host__ __device__ constexpr int dg_stage_slot_bytes(int C) { return C * 512 * dg_item_words(C); }
+__host__ __device__ constexpr int dg_stages(int C) {
+#ifdef DG_STAGE_BYTES
+    return DG_STAGE_BYTES / dg_stage_slot_bytes(C) < DG_MIN_STAGES ? DG_MIN_STAGES
+         : (DG_STAGE_BYTES / dg_stage_slot_bytes(C) > 12 ? 12 : DG_STAGE_BYTES / dg_stage_slot_bytes(C));
+#else
+    return C <= 3 ? 4 : (C <= 5 ? 3 : (C <= 8 ? 2 : 4));     // 16 / 12 / 12 / 15 / 12 / 14 / 16 KB per warp for C = 2..8
+#endif
+}
 
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dg_smem_u32(dst_smem)), "l"(src) : "memory");
@@ -82,13 +109,15 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
                                          const int *cum, const double *ff, double *stage, int lane, int wl, int NWL,
                                          double (&mm)[J], int (&ee)[J], unsigned &bad, double (&ls)[J]) {
     constexpr int JP = (J + 1) & ~1;
+    constexpr int IW = dg_item_words(KC > 0 ? KC : DG_MAXC), IP = 32 * IW;   // 16-byte words per lane, read pairs per item
+    constexpr int kStages = dg_stages(KC > 0 ? KC : DG_MAXC);
     const int nitems = cum[Tc];
     const int kmax = KC > 0 ? KC : C;
     const int per = (nitems + NWL - 1) / NWL;
     const int q0 = min(wl * per, nitems), q1 = min(q0 + per, nitems);
     if (q0 >= q1) return;
-    double2 *mystage = reinterpret_cast<double2 *>(stage) + lane;     // [stage][k][32 lanes]
-    // issue cursor (W_STAGED): item qi of time point ti, lane's pair ip of inp, source word isrc
+    double2 *mystage = reinterpret_cast<double2 *>(stage) + lane;     // [stage][k][word][32 lanes]
+    // issue cursor (W_STAGED): item qi of time point ti, lane's first pair ip of inp, source word isrc
     int qi = q0, ti = 0, ip = 0, inp = 0;
     const double2 *isrc = nullptr;
     auto issue = [&](int slot) {
@@ -97,14 +126,18 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
                 while (qi >= cum[ti + 1]) ++ti;
                 const int r0 = rel[ti];
                 inp = (rel[ti + 1] - r0) >> 1;
-                ip = (qi - cum[ti]) * 32 + lane;
+                ip = (qi - cum[ti]) * IP + lane;
                 isrc = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0) + ip;
             }
-            if (ip < inp) {
 #pragma unroll
-                for (int k = 0; k < kmax; ++k) cp_async16(mystage + (slot * kmax + k) * 32, isrc + (size_t)k * inp);
+            for (int w = 0; w < IW; ++w) {
+                if (ip + 32 * w < inp) {
+#pragma unroll
+                    for (int k = 0; k < kmax; ++k)
+                        cp_async16(mystage + ((slot * kmax + k) * IW + w) * 32, isrc + 32 * w + (size_t)k * inp);
+                }
             }
-            ++qi; ip += 32; isrc += 32;
+            ++qi; ip += IP; isrc += IP;
         }
         cp_async_commit();
     };
@@ -118,11 +151,12 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
     constexpr bool FREG = (KC > 0 && KC * J <= (J > 3 ? 18 : DG_FREG_MAX));    // f of the time point held in registers
     constexpr int FR = FREG ? KC : 1;
     int it = 0, q = q0, tt = 0;
+    int islot = kStages - 1, cslot = 0;                              // ring slots of the next issue / the next item
     while (q < q1) {
         while (q >= cum[tt + 1]) ++tt;
         const int c0 = cum[tt], c1 = min(cum[tt + 1], q1);
         const int r0 = rel[tt], npairs = (rel[tt + 1] - r0) >> 1, n = ncnt[tt];
-        int p = (q - c0) * 32 + lane;
+        int p = (q - c0) * IP + lane;
         const double2 *Wt = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0) + p;
         const double *ffcol = ff + (size_t)tt * C * JP;
         double fr[FR][J];
@@ -133,62 +167,87 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
                 for (int j = 0; j < J; ++j) fr[k][j] = ffcol[k * JP + j];
             }
         }
-#pragma unroll((WMODE == W_STAGED && J <= 3) ? 2 : 1)
-        for (; q < c1; ++q, ++it, p += 32, Wt += 32) {
+#pragma unroll((WMODE == W_STAGED && J <= 3 && IW == 1) ? 2 : 1)
+        for (; q < c1; ++q, ++it, p += IP, Wt += IP) {
             if (WMODE == W_STAGED) {
-                issue((it + kStages - 1) & (kStages - 1));
+                issue(islot);
+                islot = (islot + 1 == kStages) ? 0 : islot + 1;
                 cp_async_wait<kStages - 1>();
             }
             if (p < npairs) {
-                const double2 *st = mystage + ((it & (kStages - 1)) * kmax) * 32;
-                double x0[J], x1[J];
+                const double2 *st = mystage + (cslot * kmax * IW) * 32;
+                // the IW words of this lane are independent dependency chains in one basic block; a word
+                // past the end of the time point recomputes word 0 (valid address) and is dropped below
+                bool val[IW];
+                double x0[IW][J], x1[IW][J];
 #pragma unroll
-                for (int j = 0; j < J; ++j) { x0[j] = 0.0; x1[j] = 0.0; }
+                for (int w = 0; w < IW; ++w) {
+                    val[w] = (p + 32 * w) < npairs;
+#pragma unroll
+                    for (int j = 0; j < J; ++j) { x0[w][j] = 0.0; x1[w][j] = 0.0; }
+                }
 #pragma unroll
                 for (int k = 0; k < kmax; ++k) {
-                    const double2 w = (WMODE == W_STAGED) ? st[k * 32] : Wt[(size_t)k * npairs];
-                    if (FREG) {
+                    double2 wv[IW];
 #pragma unroll
-                        for (int j = 0; j < J; ++j) {
-                            x0[j] = fma(w.x, fr[k < FR ? k : 0][j], x0[j]);
-                            x1[j] = fma(w.y, fr[k < FR ? k : 0][j], x1[j]);
-                        }
-                    } else {
+                    for (int w = 0; w < IW; ++w) {
+                        const int wo = val[w] ? w : 0;
+                        wv[w] = (WMODE == W_STAGED) ? st[(k * IW + wo) * 32] : Wt[(size_t)k * npairs + 32 * wo];
+                    }
+                    double fj[JP];
+                    if (!FREG) {
                         const double2 *f2 = reinterpret_cast<const double2 *>(ffcol + k * JP);
-                        double fj[JP];
 #pragma unroll
                         for (int u = 0; u < JP / 2; ++u) { const double2 t = f2[u]; fj[2 * u] = t.x; fj[2 * u + 1] = t.y; }
+                    }
+#pragma unroll
+                    for (int w = 0; w < IW; ++w) {
 #pragma unroll
                         for (int j = 0; j < J; ++j) {
-                            x0[j] = fma(w.x, fj[j], x0[j]);
-                            x1[j] = fma(w.y, fj[j], x1[j]);
+                            const double fv = FREG ? fr[k < FR ? k : 0][j] : fj[j];
+                            x0[w][j] = fma(wv[w].x, fv, x0[w][j]);
+                            x1[w][j] = fma(wv[w].y, fv, x1[w][j]);
                         }
                     }
                 }
-                const bool v1 = (2 * p + 1) < n;              // the pad slot of an odd block
                 if (LOGPATH) {
 #pragma unroll
-                    for (int j = 0; j < J; ++j) {
-                        ls[j] += log(x0[j]);
-                        if (v1) ls[j] += log(x1[j]);
+                    for (int w = 0; w < IW; ++w) {
+                        if (val[w]) {
+                            const bool v1 = (2 * (p + 32 * w) + 1) < n;      // the pad slot of an odd block
+#pragma unroll
+                            for (int j = 0; j < J; ++j) {
+                                ls[j] += log(x0[w][j]);
+                                if (v1) ls[j] += log(x1[w][j]);
+                            }
+                        }
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
-                        // the two reads of the pair are multiplied first: scaling by powers of two is
-                        // exact, so mant(x0 * x1) carries the same bits as mant(x0) * mant(x1); a
-                        // product that leaves the positive normal range (a zero, negative or
-                        // non-finite x, or an under/overflow) sends the round to the log path
-                        const double y1 = v1 ? x1[j] : 1.0;
-                        const double pr2 = x0[j] * y1;
+                        // the reads of this lane's words are multiplied first: scaling by powers of two is
+                        // exact, so mant(product) carries the same bits as the product of the mantissas; a
+                        // product that leaves the positive normal range (a zero, negative or non-finite x,
+                        // or an under/overflow) sends the round to the log path
+                        double pr2 = 1.0;
+                        int sg = 0;
+#pragma unroll
+                        for (int w = 0; w < IW; ++w) {
+                            const bool v1 = (2 * (p + 32 * w) + 1) < n;      // the pad slot of an odd block
+                            const double a0 = val[w] ? x0[w][j] : 1.0;
+                            const double a1 = (val[w] && v1) ? x1[w][j] : 1.0;
+                            sg |= __double2hiint(a0) | __double2hiint(a1);       // two negative x would hide each other
+                            pr2 = (w == 0) ? a0 * a1 : pr2 * (a0 * a1);
+                        }
                         const int h = __double2hiint(pr2);
                         bad |= ((unsigned)(h - 0x00100000) >= 0x7fe00000u) ? 1u : 0u;
-                        bad |= (unsigned)(__double2hiint(x0[j]) | __double2hiint(y1)) >> 31;   // two negative x would hide each other
+                        bad |= (unsigned)sg >> 31;
                         ee[j] += (h >> 20) - 1023;
                         mm[j] *= dg_mant(pr2, h);
                     }
                 }
             }
+            if (WMODE == W_STAGED) cslot = (cslot + 1 == kStages) ? 0 : cslot + 1;
             if (!LOGPATH && (it & 255) == 255) {               // keep the running products in range
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
@@ -245,8 +304,10 @@ __device__ __noinline__ void lik_warp_pass_log(const double *Wc, const int *rel,
 // ---------------------------------------------------------------------------------------
 __host__ __device__ inline int dg_geweke_state_len(int CTm) { return 4 + 5 * CTm; }
 
+// Runs on the `nwarps` warps (index `warp`) that synchronise on named barrier `bar_id`.
 __device__ __noinline__ int geweke_converged(double *gw, double *gst, int CTm, int nwarps, int warp, int lane,
-                                             TraceView tv, int m) {
+                                             TraceView tv, int m, int bar_id = 0) {
+    const int nbar = nwarps * 32;
     if (m <= 0) return 1;                                // empty series: Z is NaN, which is not > 2
     const int GC = CTm < DG_GW_COLS ? (CTm > 0 ? CTm : 1) : DG_GW_COLS;   // scratch columns per warp
     const int nA = (int)(0.1 * (double)m);
@@ -276,13 +337,13 @@ __device__ __noinline__ int geweke_converged(double *gw, double *gst, int CTm, i
             }
         }
         if (lane < GC) { g0[warp * GC + lane] = s; g1[warp * GC + lane] = q; }
-        __syncthreads();
+        dg_bar(bar_id, nbar);
         double sa = 0.0, qa = 0.0;
         if (warp == 0 && act) {
             if (nA0 > 0) { sa = SA[col]; qa = QA[col]; }
             for (int w = 0; w < nwarps; ++w) { sa += g0[w * GC + lane]; qa += g1[w * GC + lane]; }
         }
-        __syncthreads();
+        dg_bar(bar_id, nbar);
         // ---- window B: rows [mB0, m) enter, rows [iB0, iB) leave ----
         s = 0.0; q = 0.0;
         if (act) {
@@ -298,7 +359,7 @@ __device__ __noinline__ int geweke_converged(double *gw, double *gst, int CTm, i
             }
         }
         if (lane < GC) { g0[warp * GC + lane] = s; g1[warp * GC + lane] = q; }
-        __syncthreads();
+        dg_bar(bar_id, nbar);
         if (warp == 0 && act) {
             double sb = 0.0, qb = 0.0;
             if (!resetB) { sb = SB[col]; qb = QB[col]; }
@@ -313,10 +374,17 @@ __device__ __noinline__ int geweke_converged(double *gw, double *gst, int CTm, i
             if (den == 0.0) ok = 0;
             else if (fabs(meanA - meanB) / den > 2.0) ok = 0;
         }
-        __syncthreads();
+        dg_bar(bar_id, nbar);
     }
-    if (threadIdx.x == 0) { gst[0] = (double)nA; gst[1] = (double)iB; gst[2] = (double)m; gst[3] = 1.0; }
-    return __syncthreads_and(ok);
+    // every column was judged by warp 0; its verdict goes to all warps through the (now free) scratch
+    if (warp == 0) {
+        ok = __all_sync(0xffffffffu, ok);
+        if (lane == 0) { gst[0] = (double)nA; gst[1] = (double)iB; gst[2] = (double)m; gst[3] = 1.0; gw[0] = (double)ok; }
+    }
+    dg_bar(bar_id, nbar);
+    ok = (int)gw[0];
+    dg_bar(bar_id, nbar);
+    return ok;
 }
 
 // Out-of-line copies of the long math routines used on the round loop: the loop body has
@@ -332,9 +400,9 @@ __device__ __noinline__ double dg_log(double x) { return log(x); }
 //   Q = sum_c ( jump_const[c] - (d_c K^-1 d_c) / (2 jump_scale[c]) ),  d = Y_now - Y_try = -delta
 //       (model_GP.py:330-331: Q_now and Q_try are the same number; it only enters the MH
 //       exponent as ((P_try + Q) - P_now) - Q, so it is formed here, off the serial path)
-// Called by `nprod` threads (index `pt`) which must ALL call it: they synchronise on
-// __syncthreads (all_threads) or on the likelihood-warp barrier.
-__device__ __noinline__ void produce_stream(bool dev_stream, int s0, int s1, int pt, int nprod, bool all_threads,
+// Called by `nprod` threads (index `pt`) which must ALL call it: they synchronise on the named
+// barrier `bar_id` (0 with nprod = blockDim.x is __syncthreads).
+__device__ __noinline__ void produce_stream(bool dev_stream, int s0, int s1, int pt, int nprod, int bar_id,
                                             double *zring, double *dring, int RING, int C, int Tc,
                                             const double *pfac, const double *sqs, const double *kinv,
                                             const double *jcon, const double *ijs, uint64_t seed, int64_t sid,
@@ -352,7 +420,7 @@ __device__ __noinline__ void produce_stream(bool dev_stream, int s0, int s1, int
             }
             if (pt == nprod - 1) dring[(s % RING) * RL + CT] = dg_log(dg_uniform(seed, sid, (uint32_t)s));
         }
-        if (all_threads) __syncthreads(); else bar_lik(nprod);
+        dg_bar(bar_id, nprod);
         for (int s = s0; s < s1; ++s) {
             const double *z = zring + (s % DG_STREAM_BLOCK) * RL;
             double *d = dring + (s % RING) * RL;
@@ -371,7 +439,7 @@ __device__ __noinline__ void produce_stream(bool dev_stream, int s0, int s1, int
             if (pt == nprod - 1) d[CT] = dg_log(ublk[s - m_start]);
         }
     }
-    if (all_threads) __syncthreads(); else bar_lik(nprod);
+    dg_bar(bar_id, nprod);
     // per (step, c): d K^-1 d into the z ring (free now)
     const int nq = (s1 - s0) * (C - 1);
     for (int q = pt; q < nq; q += nprod) {
@@ -385,7 +453,7 @@ __device__ __noinline__ void produce_stream(bool dev_stream, int s0, int s1, int
         }
         zring[(s % DG_STREAM_BLOCK) * RL + c] = jcon[c] - (acc * ijs[c]) / 2.0;
     }
-    if (all_threads) __syncthreads(); else bar_lik(nprod);
+    dg_bar(bar_id, nprod);
     for (int s = s0 + pt; s < s1; s += nprod) {
         double Q = 0.0;
         for (int c = 0; c < C - 1; ++c) Q += zring[(s % DG_STREAM_BLOCK) * RL + c];
@@ -417,6 +485,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
                           int slot, int n_steps, double *smem, int use_tma, int cs_rt, int crank_rt) {
     const int cs = CLUSTER ? cs_rt : 1, crank = CLUSTER ? crank_rt : 0;   // compile-time 1 / 0 for ordinary launches
     constexpr int JP = (J + 1) & ~1;
+    constexpr int IPAIRS = 32 * dg_item_words(KC > 0 ? KC : DG_MAXC);   // read pairs per likelihood item
     constexpr int DT = J >= 4 ? 3 : (J >= 2 ? 2 : 1);     // levels of the speculation tree (J <= 7 nodes, heap order)
     static_assert(J >= 1 && J <= 7, "1..7 candidate nodes per round");
     constexpr int SB = DG_STREAM_BLOCK;                   // stream steps produced per batch
@@ -460,7 +529,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     const size_t wbytes = (size_t)C * r_total * sizeof(double);
     constexpr bool W_IN_SMEM = (WMODE == W_RESIDENT);
     const double *Wc = W_IN_SMEM ? Wsm : Wg;
-    double *stage = Wsm + (size_t)(wl > 0 ? wl : 0) * kStages * C * 64;   // W_STAGED: per-warp cp.async ring
+    double *stage = Wsm + (size_t)(wl > 0 ? wl : 0) * dg_stages(KC > 0 ? KC : DG_MAXC) * (dg_stage_slot_bytes(KC > 0 ? KC : DG_MAXC) / 8);   // W_STAGED: per-warp cp.async ring
 
     // ---- stage W (TMA bulk copy, asynchronous) and the small per-chain constants --------
     if (W_IN_SMEM) {
@@ -541,7 +610,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     __syncthreads();                                      // rel / ncnt visible
     if (tid == 0) {
         int a = 0;
-        for (int t = 0; t < Tc; ++t) { cum[t] = a; a += (((rel[t + 1] - rel[t]) >> 1) + 31) >> 5; }
+        for (int t = 0; t < Tc; ++t) { cum[t] = a; a += (((rel[t + 1] - rel[t]) >> 1) + IPAIRS - 1) / IPAIRS; }
         cum[Tc] = a;
     }
     if (m > 0 && s_act) { y_now = st[si]; psi_now = st[CT + si]; }
@@ -569,7 +638,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     int produced = m;                                     // ring holds steps [.., produced)
     for (int b = 0; b < RING / SB && produced < m_end; ++b) {
         const int upto = min(produced + SB, m_end);
-        produce_stream(dev_stream, produced, upto, tid, nthreads, true, zring, dring, RING, C, Tc, pfac, sqs, kinv,
+        produce_stream(dev_stream, produced, upto, tid, nthreads, 0, zring, dring, RING, C, Tc, pfac, sqs, kinv,
                        jcon, ijs, sa.seed, sid, dblk, ublk, m_start);
         produced = upto;
         __syncthreads();
@@ -869,7 +938,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         } else if (!init && produced < m_end && produced - (m + nd) <= RING - SB) {
             // the batch behind the chain is consumed: overwrite it with the next SB steps
             produce_stream(dev_stream, produced, min(produced + SB, m_end), tid - nstate, nthreads - nstate,
-                           false, zring, dring, RING, C, Tc, pfac, sqs, kinv, jcon, ijs, sa.seed, sid, dblk, ublk, m_start);
+                           3, zring, dring, RING, C, Tc, pfac, sqs, kinv, jcon, ijs, sa.seed, sid, dblk, ublk, m_start);
         }
         if (!init && produced < m_end && produced - (m + nd) <= RING - SB) produced = min(produced + SB, m_end);
         if (init) { init = false; continue; }
