@@ -30,14 +30,19 @@ constexpr int DICEGP_CHAIN_NOMEM_ = 3;
 #define DG_LB_THREADS 512                // 512 threads/SM -> up to 128 registers per thread
 #endif
 // Candidate nodes evaluated per round (= per pass over W).  Resident tiers are bound by the
-// serial part of a round: 3 nodes.  Streamed tiers are bound by the bytes of W they pull from
-// L2 / HBM every round: 6 nodes commit more steps per byte.
+// serial part of a round: 3 nodes.  Streamed tiers also pay for the bytes of W they pull from
+// L2 / HBM every round: with wide genes a 4th node commits more steps per byte than it costs.
 #ifndef DG_NODES_RESIDENT
 #define DG_NODES_RESIDENT 3
 #endif
-#ifndef DG_NODES_STREAMED
-#define DG_NODES_STREAMED 3
+// (measured per isoform count on the bench workload: 4 nodes win from C = 4 up, 5-6 nodes lose)
+__host__ __device__ constexpr int dg_nodes_streamed(int KC) {
+#ifdef DG_NODES_STREAMED
+    return DG_NODES_STREAMED;
+#else
+    return (KC >= 4 && KC <= 8) ? 4 : 3;
 #endif
+}
 template <int KC, int WMODE, bool CLUSTER = false, int NJ = DG_NODES_RESIDENT>
 __global__ void __launch_bounds__(DG_LB_THREADS, 1)
 dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__restrict__ ids, int n_ids,
@@ -475,7 +480,8 @@ void launch_classes(const dicegp_ctx *c, LaunchClass out[kTiers]) {
 
 // shared memory of a chain besides W / the staging rings; `streamed`: tiers 4-7
 size_t fixed_smem_bytes(int C, int Tc, int threads, bool streamed, int cs = 1) {
-    return (size_t)dg_layout(C, Tc, (threads + 31) / 32, streamed ? DG_NODES_STREAMED : DG_NODES_RESIDENT, cs).total * sizeof(double);
+    const int nodes = streamed ? dg_nodes_streamed(C <= 8 ? C : 0) : DG_NODES_RESIDENT;
+    return (size_t)dg_layout(C, Tc, (threads + 31) / 32, nodes, cs).total * sizeof(double);
 }
 inline int tier_cluster(int tier) { return tier < 5 ? 1 : (2 << (tier - 5)); }
 
@@ -554,14 +560,14 @@ chain_kernel_t chain_kernel_for(int kind, bool w_in_smem, bool cluster) {
     // cluster launches exist for the streamed variants only
     if (cluster) {
         switch (kind) {
-            case 0: return dicegp_chain_kernel<0, dg::W_DIRECT, true, DG_NODES_STREAMED>;
-            case 1: return dicegp_chain_kernel<2, dg::W_STAGED, true, DG_NODES_STREAMED>;
-            case 2: return dicegp_chain_kernel<3, dg::W_STAGED, true, DG_NODES_STREAMED>;
-            case 3: return dicegp_chain_kernel<4, dg::W_STAGED, true, DG_NODES_STREAMED>;
-            case 4: return dicegp_chain_kernel<5, dg::W_STAGED, true, DG_NODES_STREAMED>;
-            case 5: return dicegp_chain_kernel<6, dg::W_STAGED, true, DG_NODES_STREAMED>;
-            case 6: return dicegp_chain_kernel<7, dg::W_STAGED, true, DG_NODES_STREAMED>;
-            default: return dicegp_chain_kernel<8, dg::W_STAGED, true, DG_NODES_STREAMED>;
+            case 0: return dicegp_chain_kernel<0, dg::W_DIRECT, true, dg_nodes_streamed(0)>;
+            case 1: return dicegp_chain_kernel<2, dg::W_STAGED, true, dg_nodes_streamed(2)>;
+            case 2: return dicegp_chain_kernel<3, dg::W_STAGED, true, dg_nodes_streamed(3)>;
+            case 3: return dicegp_chain_kernel<4, dg::W_STAGED, true, dg_nodes_streamed(4)>;
+            case 4: return dicegp_chain_kernel<5, dg::W_STAGED, true, dg_nodes_streamed(5)>;
+            case 5: return dicegp_chain_kernel<6, dg::W_STAGED, true, dg_nodes_streamed(6)>;
+            case 6: return dicegp_chain_kernel<7, dg::W_STAGED, true, dg_nodes_streamed(7)>;
+            default: return dicegp_chain_kernel<8, dg::W_STAGED, true, dg_nodes_streamed(8)>;
         }
     }
     (void)w_in_smem;
@@ -679,7 +685,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                         if (thr * kk > DG_LB_THREADS) continue;
                         size_t need = fixed_smem_bytes(maxC, maxTc, thr, true) + 1024;
                         if (kind != 0) need += (size_t)nwl * dg::dg_stages(maxC) * dg::dg_stage_slot_bytes(maxC);
-                        if (need * kk > 233472) continue;
+                        if (need * kk > 233472 || need - 1024 + 127 > c->smem_optin - c->static_smem) continue;
                         // at least 8 streaming warps per SM, then as many chains as possible (their serial
                         // phases overlap), then more warps
                         const int score = latency_mode ? nwl : std::min(kk * nwl, 8) * 100 + kk * 10 + nwl;
@@ -696,7 +702,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                     if (thr > DG_LB_THREADS) break;
                     size_t need = fixed_smem_bytes(maxC, maxTc, thr, true, cs) + 1024;
                     if (kind != 0) need += (size_t)nwl * dg::dg_stages(maxC) * dg::dg_stage_slot_bytes(maxC);
-                    if (need > 233472) break;
+                    if (need > 233472 || need - 1024 + 127 > c->smem_optin - c->static_smem) break;
                     best = thr;
                 }
                 if (best < 0) return c->fail(DICEGP_ERR_LIMIT, "chain has too many latent values for the cluster tier");
