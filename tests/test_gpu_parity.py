@@ -168,3 +168,31 @@ def test_large_gene_takes_cluster_tier_and_matches_oracle():
     got = Psi_GP_MH(R, L, P, **kw)
     compare(got, ref)
     assert got[5] > 0
+
+
+@pytest.mark.parametrize("g", [3, 4, 5])
+def test_bias_weighted_config_step_parity(g):
+    """BASELINE config 4: per-read bias weights folded into prob (bias_utils.py:140-173 feeds
+    tran_utils.py:181-186); isoform count as the config draws it, 8 time points."""
+    R, L, P = synth.gene_matrices("bias", g, reads=400)
+    T = len(R)
+    kw = dict(theta1=3.0, theta2=float(synth.default_theta2(np.arange(T))), M=500, initial=300, gap=100,
+              randomS=400 + g)
+    with np.errstate(all="ignore"):
+        ref = orc.psi_gp_mh([r.copy() for r in R], [l.copy() for l in L], [p.copy() for p in P], **kw)
+    got = Psi_GP_MH(R, L, P, **kw)
+    compare(got, ref)
+
+
+@pytest.mark.parametrize("g", [0, 1, 6, 10])
+def test_human_scale_config_step_parity(g):
+    """BASELINE config 5: 4 time points with heavy-tailed, ragged read counts (46 ... 96k reads
+    per time point in these genes) and 2-10 isoforms, exactly as the config draws them."""
+    R, L, P = synth.gene_matrices("human", g)
+    T = len(R)
+    kw = dict(theta1=3.0, theta2=float(synth.default_theta2(np.arange(T))), M=260, initial=200, gap=50,
+              randomS=500 + g)
+    with np.errstate(all="ignore"):
+        ref = orc.psi_gp_mh([r.copy() for r in R], [l.copy() for l in L], [p.copy() for p in P], **kw)
+    got = Psi_GP_MH(R, L, P, **kw)
+    compare(got, ref)
