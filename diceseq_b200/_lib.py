@@ -24,7 +24,7 @@ SYMBOLS = (
     "dicegp_main_chains_from_prerun", "dicegp_run_host_stream", "dicegp_run_device_stream",
     "dicegp_chain_status", "dicegp_download_trace", "dicegp_posterior_summary",
     "dicegp_last_run_stats", "dicegp_set_trace_budget", "dicegp_set_prerun_chains",
-    "dicegp_timer_start", "dicegp_timer_stop", "dicegp_counters",
+    "dicegp_timer_start", "dicegp_timer_stop", "dicegp_counters", "dicegp_eval_loglik",
 )
 
 
@@ -211,6 +211,18 @@ class Context:
         self._check(self.lib.dicegp_run_device_stream(self._h, C.c_uint64(int(seed)), _p(sid, C.c_int64)))
 
     # -- results -------------------------------------------------------------------------
+    def eval_loglik(self, gene, y, t0=0):
+        """lik[t] = sum_n log(W_t[n,:] . fsi[:,t]) of the state y (C x Tc) for the time points
+        [t0, t0+Tc) of an uploaded gene (dicegp_eval_loglik; model_GP.py:335-345)."""
+        y = _f64(y)
+        Tc = y.shape[1]
+        if y.shape[0] != int(self.gene_C[gene]):
+            raise ValueError("y must have one row per isoform of the gene")
+        lik = np.empty(Tc)
+        self._check(self.lib.dicegp_eval_loglik(self._h, int(gene), int(t0), int(Tc), _p(y, C.c_double),
+                                                _p(lik, C.c_double)))
+        return lik
+
     def chain_status(self, chain_ids=None):
         if chain_ids is None:
             chain_ids = np.arange(len(self.chain_shapes))

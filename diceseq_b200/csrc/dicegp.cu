@@ -185,6 +185,58 @@ __global__ void dicegp_gather_rows_kernel(ChainTab ct, int chain, int rowlen, in
 }
 
 // ---------------------------------------------------------------------------------------
+// Log-likelihood of ONE given latent state (model_GP.py:335-345), for chains whose proposal
+// stream depends on the chain state and are therefore driven step by step from the host
+// (theta2 sampling, model_GP.py:317-326).  grid = (blocks per time point, Tc): a block forms
+//   e = exp(y[:, t]), f = len*e / sum(len*e)       (= fsi of model_GP.py:336-337)
+// for its time point, sums log(sum_k W_t[n,k] f[k]) over its slice of the reads with real
+// logs (so that -inf / NaN propagate like np.log(...).sum()), and the last block to finish
+// a time point adds the per-block partial sums in block order (deterministic).
+// ---------------------------------------------------------------------------------------
+#define DG_EVAL_THREADS 256
+__global__ void __launch_bounds__(DG_EVAL_THREADS)
+dicegp_loglik_kernel(GeneTab gt, int g, int t0, const double *__restrict__ y, int Tc,
+                     double *__restrict__ partial, unsigned *__restrict__ done, double *__restrict__ lik_out) {
+    __shared__ double f[DG_MAXC];
+    __shared__ double red[DG_EVAL_THREADS / 32];
+    __shared__ bool last;
+    const int tt = blockIdx.y, t = t0 + tt, C = gt.C[g], T = gt.T;
+    const int32_t *roff = gt.roff + (size_t)g * (T + 1) + t;
+    const int n = gt.ncnt[(size_t)g * T + t], padn = roff[1] - roff[0];
+    const double *Wt = gt.W + gt.woff[g] + (size_t)C * roff[0];
+    if (threadIdx.x == 0) {
+        const double *len = gt.len + gt.lenoff[g] + (size_t)t * C;
+        double tot = 0.0;
+        for (int k = 0; k < C; ++k) { f[k] = len[k] * exp(y[(size_t)k * Tc + tt]); tot += f[k]; }
+        for (int k = 0; k < C; ++k) f[k] = f[k] / tot;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double x = 0.0;
+        for (int k = 0; k < C; ++k) x = fma(__ldg(Wt + (size_t)k * padn + i), f[k], x);
+        acc += log(x);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < DG_EVAL_THREADS / 32; ++w) s += red[w];
+        partial[(size_t)tt * gridDim.x + blockIdx.x] = s;
+        __threadfence();
+        last = atomicAdd(done + tt, 1u) == gridDim.x - 1;
+        if (last) {
+            __threadfence();
+            double tot = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) tot += __ldcg(partial + (size_t)tt * gridDim.x + b);
+            lik_out[tt] = tot;
+            done[tt] = 0;                   // ready for the next call
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Posterior summary of one chain per block (run_utils.py:14-30, 125-129):
 //   burn-in b = int(m/4); psi_mean = Psi_all[b:].mean(0) (rows added sequentially, like
 //   numpy's axis-0 reduction); 95% interval = order statistics sorted[-k], sorted[k],
@@ -405,6 +457,8 @@ struct dicegp_ctx {
     DevBuf<double> ddelta, du, dvar;
     DevBuf<int> dqueue;
     DevBuf<double> smean, sci, slik;       // posterior summary scratch
+    DevBuf<double> deval;                  // eval_loglik scratch: y | per-block partial sums | lik
+    DevBuf<unsigned> deval_done;
     DevBuf<int64_t> soff;
     DevBuf<int32_t> sids;
     DevBuf<unsigned long long> dprof;
@@ -876,7 +930,7 @@ int dicegp_destroy(dicegp_ctx *c) {
     c->dgather.release(); c->cst_off.release(); c->cstream_id.release();
     c->cprior.release(); c->cpool.release(); c->ctrace.release(); c->cst.release();
     c->dids.release(); c->ddoff.release(); c->ddelta.release(); c->du.release(); c->dvar.release();
-    c->dqueue.release();
+    c->dqueue.release(); c->deval.release(); c->deval_done.release();
     c->smean.release(); c->sci.release(); c->slik.release(); c->soff.release(); c->sids.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1205,6 +1259,35 @@ int dicegp_run_device_stream(dicegp_ctx *c, uint64_t seed, const int64_t *stream
         todo.swap(rest);
     }
     c->last_ms = ms; c->last_launches = launches; c->last_evals = evals; c->last_steps = steps;
+    return DICEGP_OK;
+}
+
+int dicegp_eval_loglik(dicegp_ctx *c, int32_t gene, int32_t t0, int32_t Tc, const double *y, double *lik) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (c->G == 0) return c->fail(DICEGP_ERR_STATE, "eval_loglik: no genes uploaded");
+    if (gene < 0 || gene >= c->G || t0 < 0 || Tc <= 0 || t0 + Tc > c->T || !y || !lik)
+        return c->fail(DICEGP_ERR_ARG, "eval_loglik: gene / time range outside the batch, or NULL buffer");
+    DG_CUDA(c, cudaSetDevice(c->device));
+    const int C = c->hC[gene];
+    int max_n = 1;
+    for (int t = t0; t < t0 + Tc; ++t) max_n = std::max(max_n, c->hncnt[(size_t)gene * c->T + t]);
+    // enough blocks to cover the reads four deep, at most two waves of the device over the time points
+    int nblk = (max_n + 4 * DG_EVAL_THREADS - 1) / (4 * DG_EVAL_THREADS);
+    nblk = std::max(1, std::min(nblk, std::max(1, 2 * c->sm_count / Tc)));
+    const size_t need = (size_t)C * Tc + (size_t)Tc * nblk + Tc;      // y | partial sums | lik
+    DG_CUDA(c, c->deval.resize(need));
+    if (c->deval_done.n < (size_t)c->T) {
+        DG_CUDA(c, c->deval_done.resize(c->T));
+        DG_CUDA(c, cudaMemsetAsync(c->deval_done.p, 0, c->deval_done.n * sizeof(unsigned), c->stream));
+    }
+    double *dy = c->deval.p, *dpart = dy + (size_t)C * Tc, *dlik = dpart + (size_t)Tc * nblk;
+    DG_CUDA(c, cudaMemcpyAsync(dy, y, (size_t)C * Tc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dicegp_loglik_kernel<<<dim3(nblk, Tc), DG_EVAL_THREADS, 0, c->stream>>>(make_gene_tab(c), gene, t0, dy, Tc, dpart,
+                                                                            c->deval_done.p, dlik);
+    DG_CUDA(c, cudaGetLastError());
+    ++c->total_launches;
+    DG_CUDA(c, cudaMemcpyAsync(lik, dlik, (size_t)Tc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    DG_CUDA(c, cudaStreamSynchronize(c->stream));
     return DICEGP_OK;
 }
 

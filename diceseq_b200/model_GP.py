@@ -7,7 +7,9 @@ the host side of the loop: input cleaning (in place), the GP kernel and its nump
 inverse / determinant, and -- because the reference consumes numpy's global legacy
 MT19937 state -- the proposal / uniform stream, generated in the reference's exact
 interleaving and shipped to the device in chunks that end on the
-convergence-check steps.  There is no CPU fallback for the loop itself.
+convergence-check steps.  There is no CPU fallback for the loop itself.  With
+`theta2=None` the stream depends on the chain state; that mode is driven step by step from
+the host with the read likelihood evaluated on the device (theta2_mode.py).
 
 `normal_pdf`, `GP_K`, `Geweke_Z` are the small public helpers the reference exports next
 to the sampler (diceseq/__init__.py:15); they stay host functions.
@@ -177,13 +179,18 @@ def Psi_GP_MH(R_mat, len_isos, prob_isos, X=None, Ymean=None, var=None, theta1=3
     if randomS is not None:
         np.random.seed(randomS)
     clean_inputs(R_mat, len_isos, prob_isos)
-    if theta2 is None:
-        raise NotImplementedError(
-            "theta2=None (sampling theta2, model_GP.py:317-326) is not offloaded yet; the "
-            "diceseq CLI never takes this branch unless --thetas x learn is given")
     if var is None:
         var = 0.05 * np.ones(C - 1)
     M, initial, gap = int(M), int(initial), int(gap)
+    if theta2 is None:
+        # theta2 is sampled too (model_GP.py:317-326): state-dependent stream, host-driven
+        # steps with the read likelihood on the device -- see theta2_mode.py
+        from .theta2_mode import sample_with_theta2
+        W_list = [R_mat[t] * prob_isos[t] for t in range(T)]
+        ctx = get_context(device)
+        ctx.upload_genes(pack_genes([(W_list, [np.asarray(l, dtype=np.float64) for l in len_isos])]))
+        return sample_with_theta2(ctx, T, C, X, Ymean, var, theta1, M, initial, gap, theta2_std,
+                                  theta2_low, theta2_up)
 
     consts = ChainConstants(X, C, var, theta1, theta2)
     W_list = [R_mat[t] * prob_isos[t] for t in range(T)]

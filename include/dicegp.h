@@ -206,6 +206,21 @@ int dicegp_posterior_summary(dicegp_ctx *ctx, int32_t n, const int32_t *chain_id
                              double *psi_mean, double *psi_ci, const int64_t *out_off,
                              double *lik_marg);
 
+/*
+ * Log-likelihood of ONE given latent state, per time point (model_GP.py:335-345):
+ *   psi[:,t] = softmax(y[:,t]); fsi = len_t*psi/sum(len_t*psi);
+ *   lik[t]   = sum_n log( sum_k W_t[n,k] * fsi[k,t] )        for t in [t0, t0+Tc) of `gene`.
+ * y: C x Tc row-major (host), lik: Tc doubles (host); synchronous.  The caller adds the
+ * time points in ascending order like model_GP.py:338-345.  This is the device half of
+ * the theta2-sampling mode (theta2=None, model_GP.py:317-326): there the number of
+ * normals the reference draws per step depends on the chain state (rejection loop of the
+ * truncated random walk) and the proposal covariance changes with every theta2_try, so
+ * the stream cannot be produced ahead of the chain; the host proposes step by step and
+ * the device evaluates the reads.  Needs dicegp_upload_genes only (no chains).
+ */
+int dicegp_eval_loglik(dicegp_ctx *ctx, int32_t gene, int32_t t0, int32_t Tc, const double *y,
+                       double *lik);
+
 /* Device time (ms, CUDA events on the launch stream) and kernel launches of the most
  * recent run_* call, and the MH steps x reads it evaluated.  For bench.py. */
 int dicegp_last_run_stats(dicegp_ctx *ctx, double *kernel_ms, int64_t *launches,

@@ -196,3 +196,48 @@ def test_human_scale_config_step_parity(g):
         ref = orc.psi_gp_mh([r.copy() for r in R], [l.copy() for l in L], [p.copy() for p in P], **kw)
     got = Psi_GP_MH(R, L, P, **kw)
     compare(got, ref)
+
+
+def test_theta2_sampling_mode_matches_reference_golden():
+    """`theta2=None` (model_GP.py:317-326): host-driven steps, read likelihood on the device.
+    Same m / cnt / theta2 trace as the unmodified reference, traces within 1e-12."""
+    R, L, P, kw, z = load_golden("learn_c2")
+    got = Psi_GP_MH(R, L, P, **kw)
+    ref = (z["Psi_all"], z["Y_all"], z["theta2_all"], z["Pro_all"], z["Lik_all"], int(z["cnt"]), int(z["m"]))
+    compare(got, ref)
+
+
+def test_theta2_sampling_mode_fails_like_reference_for_three_isoforms():
+    """The reference leaves cov_try[:, :, 1:] at zero in this mode and dies in np.linalg.inv
+    (SURVEY.md Appendix B); same exception here."""
+    R, L, P = synth.gene_matrices("timeseries", 8, reads=50, T=2, C=3)
+    with pytest.raises(np.linalg.LinAlgError):
+        Psi_GP_MH(R, L, P, theta1=3.0, theta2=None, M=50, initial=30, gap=10, randomS=1)
+
+
+def test_eval_loglik_matches_numpy_on_ragged_large_gene():
+    """dicegp_eval_loglik on a human-scale gene (ragged read counts, several blocks per time
+    point) and on a state with a zero likelihood row (-inf like numpy)."""
+    from diceseq_b200.model_GP import get_context
+    from diceseq_b200.packer import pack_genes
+    W, lens = synth.gene_W("human", 0)
+    ctx = get_context(0)
+    ctx.upload_genes(pack_genes([(W, lens)]))
+    rng = np.random.RandomState(3)
+    C, T = W[0].shape[1], len(W)
+    for _ in range(3):
+        Y = rng.normal(0, 1.5, size=(C, T))
+        Y[-1] = 0
+        got = ctx.eval_loglik(0, Y)
+        for t in range(T):
+            e = np.exp(Y[:, t]); psi = e / e.sum()
+            f = lens[t] * psi / np.sum(lens[t] * psi)
+            ref = np.log(W[t] @ f).sum()
+            assert abs(got[t] - ref) <= 1e-12 * abs(ref)
+    # a sub-range of the time points
+    got = ctx.eval_loglik(0, Y[:, 1:3], t0=1)
+    full = ctx.eval_loglik(0, Y)
+    assert np.allclose(got, full[1:3], rtol=1e-13, atol=0)      # (block partition may differ)
+    Y[:, 0] = [800.0] + [0.0] * (C - 1)         # exp overflows: nan like the reference's softmax
+    with np.errstate(all="ignore"):
+        assert not np.isfinite(ctx.eval_loglik(0, Y)[0])
