@@ -110,6 +110,22 @@ def _i64(a):
     return np.ascontiguousarray(a, dtype=np.int64)
 
 
+class ChainShapes:
+    """(C, Tc, M) of every installed chain, as arrays (80k pre-run chains per batch: no
+    per-chain Python objects on the sampling path); indexes like a list of tuples."""
+
+    def __init__(self, C_, Tc, M):
+        self.C = np.asarray(C_, dtype=np.int64)
+        self.Tc = np.broadcast_to(np.asarray(Tc, dtype=np.int64), self.C.shape)
+        self.M = np.broadcast_to(np.asarray(M, dtype=np.int64), self.C.shape)
+
+    def __len__(self):
+        return self.C.size
+
+    def __getitem__(self, i):
+        return int(self.C[i]), int(self.Tc[i]), int(self.M[i])
+
+
 class Context:
     """One handle per GPU (dicegp_create / dicegp_destroy)."""
 
@@ -122,7 +138,7 @@ class Context:
         self.device = device
         self.gene_C = None
         self.T = 0
-        self.chain_shapes = []      # (C, Tc, M) per chain
+        self.chain_shapes = ChainShapes([], 1, 1)      # (C, Tc, M) per chain
 
     def close(self):
         if self._h:
@@ -160,18 +176,19 @@ class Context:
             _p(W, C.c_double), W.size, _p(lens, C.c_double), lens.size))
         self.gene_C = n_iso.copy()
         self.T = packed.T
-        self.chain_shapes = []
+        self.chain_shapes = ChainShapes([], 1, 1)
 
     # -- chains --------------------------------------------------------------------------
     def set_chains(self, descs, pool):
         arr = (ChainDesc * len(descs))(*descs)
         pool = _f64(pool)
         self._check(self.lib.dicegp_set_chains(self._h, len(descs), arr, _p(pool, C.c_double), pool.size))
-        self.chain_shapes = [(int(self.gene_C[d.gene]), d.Tc, d.M) for d in descs]
+        self.chain_shapes = ChainShapes([self.gene_C[d.gene] for d in descs], [d.Tc for d in descs],
+                                        [d.M for d in descs])
 
     def set_prerun_chains(self, theta1, var0=0.1, M=100, initial=100, gap=50):
         self._check(self.lib.dicegp_set_prerun_chains(self._h, float(theta1), float(var0), M, initial, gap))
-        self.chain_shapes = [(int(c), 1, M) for c in self.gene_C for _ in range(self.T)]
+        self.chain_shapes = ChainShapes(np.repeat(self.gene_C, self.T), 1, M)
 
     def timer_start(self):
         self._check(self.lib.dicegp_timer_start(self._h))
@@ -194,7 +211,7 @@ class Context:
         self._check(self.lib.dicegp_main_chains_from_prerun(
             self._h, M, initial, gap, float(theta1), _p(kinv, C.c_double),
             _p(pf, C.c_double), float(prior_const), _p(var, C.c_double)))
-        self.chain_shapes = [(int(c), self.T, M) for c in self.gene_C]
+        self.chain_shapes = ChainShapes(self.gene_C, self.T, M)
         return var
 
     # -- running -------------------------------------------------------------------------
@@ -251,7 +268,7 @@ class Context:
         if chain_ids is None:
             chain_ids = np.arange(len(self.chain_shapes))
         ids = _i32(chain_ids)
-        sizes = np.array([self.chain_shapes[i][0] * self.chain_shapes[i][1] for i in ids], dtype=np.int64)
+        sizes = self.chain_shapes.C[ids] * self.chain_shapes.Tc[ids]
         off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         mean = np.empty(int(off[-1]))
         ci = np.empty(2 * int(off[-1]))

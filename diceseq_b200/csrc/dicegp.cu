@@ -713,7 +713,9 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     // big tiers first: the 1-block-per-SM and streaming launches carry most of the work
     const int tier_order[kTiers] = {7, 6, 5, 4, 3, 2, 1, 0};
     for (int to = 0; to < kTiers; ++to) {
-        for (int kind = 0; kind < kKinds; ++kind) {
+        for (int kind_i = 0; kind_i < kKinds; ++kind_i) {
+            // straggler pass: many isoforms first (most of the chains that use all M steps are those)
+            const int kind = latency_mode ? (kind_i == kKinds - 1 ? 0 : kKinds - 1 - kind_i) : kind_i;
             const int tier = tier_order[to];
             const int k = tier * kKinds + kind;
             const int n_ids = (int)by_group[k].size();
