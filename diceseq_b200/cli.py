@@ -8,8 +8,10 @@ pool, `-p`), (2) GPU: all multi-isoform genes sampled in batches by `BatchSample
 
 Differences, all deliberate: single-isoform genes get psi = 1 rows instead of crashing the
 worker; `.sample.gz` is written in text mode (Appendix B #11);
-`--bias` modes other than `unif` and `--thetas x learn` are refused (need a FASTA / are
-not offloaded); extra flags `--device`, `--seed`, `--batch`.
+`--bias` modes other than `unif` are refused (they need a reference FASTA and a bias file);
+`--thetas x learn` runs host-driven chains, one gene at a time, with the likelihood on the GPU
+(theta2_mode.py) and -- like the reference's sampler -- only handles two-isoform genes;
+extra flags `--device`, `--seed`, `--batch`.
 
     python -m diceseq_b200.cli -a anno.gtf -s t1.bam---t2.bam---t3.bam -t 1.5,2.5,5 -o out/joint --add_premRNA
 """
@@ -103,8 +105,7 @@ def main(argv=None):
     if theta2 is None or theta2 in ("None", "Auto", "auto"):
         theta2 = ((max(X) - min(X) + 0.1) / 3.0) ** 2                # diceseq.py:169
     elif theta2 == "learn":
-        print("[DICEseq] Error: --thetas x learn (sampling theta2) is not supported by the GPU sampler.")
-        sys.exit(1)
+        theta2 = None                                                # diceseq.py:170-171
     else:
         theta2 = max(0.00001, float(theta2))
     if options.bias_args[0] != "unif":
@@ -134,6 +135,31 @@ def main(argv=None):
     multi = [i for i, g in enumerate(genes) if g.tranNum > 1]
     results = {}
     samples = {}
+    sample_theta2 = {}
+    if theta2 is None:
+        # theta2 sampled per gene (model_GP.py:317-326): the proposal stream depends on the chain
+        # state, so these chains are host-driven, one gene after the other, with the likelihood on
+        # the GPU.  The reference's sampler only survives this mode for two-isoform genes; its
+        # worker pool drops the others silently (diceseq.py:230-233), here they are named.
+        from .run_utils import sample_gene_theta2
+        if options.seed is not None:
+            np.random.seed(options.seed)
+        dropped = []
+        for n_done, i in enumerate(multi):
+            R_all, len_all, prob_all, _count = inputs[i]
+            try:
+                r = sample_gene_theta2(R_all, len_all, prob_all, X, theta1, Mmax, Mmin, Mgap, sample_num,
+                                       device=options.device)
+            except np.linalg.LinAlgError:
+                dropped.append(genes[i].geneID)
+                continue
+            results[i], samples[i], sample_theta2[i] = r, r.Y_tail, r.theta2_mean
+            sys.stdout.write("\r[DICEseq] %d / %d genes sampled in %.1f sec." % (n_done + 1, len(multi), time.time() - start_time))
+            sys.stdout.flush()
+        if dropped:
+            print("\n[DICEseq] Warning: --thetas x learn only works for two-isoform genes (as in the reference); "
+                  "no output for %d genes: %s" % (len(dropped), ",".join(dropped[:20]) + ("..." if len(dropped) > 20 else "")))
+        multi = []
     chunks = [multi[b0:b0 + options.batch] for b0 in range(0, len(multi), options.batch)]
 
     def batches():
@@ -195,13 +221,15 @@ def main(argv=None):
         for i, g in enumerate(genes):
             count = inputs[i][3]
             if g.tranNum > 1:
+                if i not in results:
+                    continue                                         # dropped in theta2-sampling mode
                 r = results[i]
                 psi_mean, psi_95, lik_marg = r.psi_mean, r.psi_95, r.lik_marg
             else:
                 psi_mean, psi_95, lik_marg = single_isoform_result(T)
             fid1.write(format_dice_lines(g, X, count, TOTAL_READ, psi_mean, psi_95, lik_marg))
             if fid2 is not None and g.tranNum > 1:
-                fid2.write(format_sample_lines(g, theta2, samples[i], g.tranNum))
+                fid2.write(format_sample_lines(g, sample_theta2.get(i, theta2), samples[i], g.tranNum))
         if fid2 is not None:
             fid2.close()
     print("\n[DICEseq] done: %s.dice (%d genes, %.1f sec)." % (options.out_file, len(genes), time.time() - start_time))

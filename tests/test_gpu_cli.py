@@ -87,3 +87,28 @@ def test_cli_in_several_batches_gives_the_same_file(tmp_path):
                   "--add_premRNA", "-p", "1", "--mcmc", "5", "3000", "1000", "100", "--seed", "11"] + extra)
         outs.append((open(out + ".dice").read(), gzip.open(out + ".sample.gz", "rt").read()))
     assert outs[0] == outs[1]
+
+
+def test_theta2_sampling_mode_from_the_command_line(tmp_path):
+    """`--thetas 3 learn` (diceseq.py:170-171): every gene's chains sample theta2 too; host-driven
+    steps with the likelihood on the GPU.  The demo genes have two isoforms each (with pre-mRNA),
+    the only case the reference's sampler handles in this mode.  Ratios stay within 0.1 of the
+    fixed-theta2 expectation (the GP length scale only smooths across the three time points)."""
+    from diceseq_b200 import cli
+    out = str(tmp_path / "learn")
+    sams = "---".join(os.path.join(DATA, "reads_t%d.sorted.bam" % t) for t in (1, 2, 3))
+    cli.main(["-a", os.path.join(DATA, "yeast_RNA_splicing.gtf"), "-s", sams, "-o", out, "-p", "1", "--add_premRNA",
+              "--time_seq=1.5,2.5,5", "--thetas", "3", "learn", "--mcmc", "3", "4000", "1000", "100", "--seed", "5"])
+    h1, r1 = _read_dice(out + ".dice")
+    h2, r2 = _read_dice(os.path.join(DATA, "joint.dice"))
+    assert h1 == h2 and [r[0] for r in r1] == [r[0] for r in r2]
+    for k in range(0, len(r1), 2):
+        psi = EXPECT["joint_%s_psi" % r1[k][1]]
+        for c in (0, 1):
+            va = np.array(r1[k + c][4:], float).reshape(-1, 4)
+            assert np.abs(va[:, 1] - psi[c]).max() < 0.1, (r1[k + c][0], va[:, 1], psi[c])
+            assert (va[:, 2] <= va[:, 1] + 1e-9).all() and (va[:, 1] <= va[:, 3] + 1e-9).all()
+    txt = gzip.open(out + ".sample.gz", "rt").read().split("\n")
+    head = txt[3].split("|")
+    assert head[0] == "@YMR116C" and 0.00001 <= float(head[2]) <= 100        # mean of the sampled theta2 trace
+    assert len(txt[4].split(";")) == 3
