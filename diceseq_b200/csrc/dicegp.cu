@@ -1361,9 +1361,9 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
     if (smem > c->smem_optin - 4096) return c->fail(DICEGP_ERR_LIMIT, "posterior_summary: M too large for the shared-memory radix select");
     // Launch groups by rows kept: the radix select holds one column in shared memory, so
     // short chains (the bulk) run 8 blocks per SM and only the long ones need a whole SM.
-    std::vector<int32_t> ids(chain_ids, chain_ids + n), nr(n);
+    std::vector<int32_t> ids(chain_ids, chain_ids + n), nr(n), mr(n);
     {
-        int rc = dicegp_chain_status(c, n, ids.data(), nullptr, nr.data(), nullptr, nullptr, nullptr);
+        int rc = dicegp_chain_status(c, n, ids.data(), mr.data(), nr.data(), nullptr, nullptr, nullptr);
         if (rc != DICEGP_OK) return rc;
     }
     const int bounds[4] = {3072, 7168, 14336, 0x7fffffff};
@@ -1373,7 +1373,8 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
         gstart[k] = (int)order.size();
         for (int i = 0; i < n; ++i) {
             const int lo = k == 0 ? -1 : bounds[k - 1];
-            if (nr[i] > lo && nr[i] <= bounds[k]) { order.push_back(i); gmax[k] = std::max(gmax[k], nr[i]); }
+            // shared memory holds the rows kept after the burn-in int(m/4) (run_utils.py:125)
+            if (nr[i] > lo && nr[i] <= bounds[k]) { order.push_back(i); gmax[k] = std::max(gmax[k], nr[i] - (mr[i] > 0 ? mr[i] >> 2 : 0)); }
         }
     }
     gstart[4] = (int)order.size();
@@ -1393,14 +1394,24 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
         if ((e = cudaMemcpyAsync(doff.p, off_sorted.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(dids.p, ids_sorted.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
         if ((e = cudaFuncSetAttribute(dicegp_summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - 4096))) != cudaSuccess) break;
-        for (int k = 0; k < 4 && e == cudaSuccess; ++k) {
+        // the size classes run side by side (the few long chains keep only some SMs busy, for as long
+        // as the thousands of short ones take all together): longest first, one stream each.
+        // (Measured and dropped: fetching four trace columns per sweep over the rows -- a quarter of the
+        // DRAM traffic, but four columns of keys in shared memory leave too few blocks per SM; and
+        // finishing a selection early once its bucket holds <= 32 keys -- no gain.)
+        if ((e = cudaEventRecord(c->ev_fork, c->stream)) != cudaSuccess) break;
+        for (int k = 3; k >= 0 && e == cudaSuccess; --k) {
             const int cnt = gstart[k + 1] - gstart[k];
             if (cnt == 0) continue;
             const size_t sm = (size_t)gmax[k] * sizeof(unsigned long long);
-            dicegp_summary_kernel<<<cnt, DG_SUM_THREADS, sm, c->stream>>>(make_gene_tab(c), make_chain_tab(c), dids.p + gstart[k],
-                                                                          dmean.p, dci.p, doff.p + gstart[k], dlik.p + gstart[k]);
+            cudaStream_t st = c->class_stream[k];
+            if ((e = cudaStreamWaitEvent(st, c->ev_fork, 0)) != cudaSuccess) break;
+            dicegp_summary_kernel<<<cnt, DG_SUM_THREADS, sm, st>>>(make_gene_tab(c), make_chain_tab(c), dids.p + gstart[k],
+                                                                   dmean.p, dci.p, doff.p + gstart[k], dlik.p + gstart[k]);
             ++c->total_launches;
-            e = cudaGetLastError();
+            if ((e = cudaGetLastError()) != cudaSuccess) break;
+            if ((e = cudaEventRecord(c->ev_join[k], st)) != cudaSuccess) break;
+            e = cudaStreamWaitEvent(c->stream, c->ev_join[k], 0);
         }
         if (e != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(psi_mean, dmean.p, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
