@@ -19,6 +19,7 @@ constexpr int DICEGP_CHAIN_EXHAUSTED_ = 2;
 constexpr int DICEGP_CHAIN_NOMEM_ = 3;
 }  // namespace dg
 #include "dicegp_chain.cuh"
+#include "dicegp_prerun.cuh"
 
 // =======================================================================================
 // kernels
@@ -450,6 +451,7 @@ struct dicegp_ctx {
     DevBuf<double> dgather;
     DevBuf<double> cprior, cpool, ctrace, cst;
     bool have_stream_id = false;
+    bool chains_fresh = false;           // installed and not advanced yet
 
     // run scratch
     DevBuf<int32_t> dids;
@@ -644,6 +646,7 @@ chain_kernel_t chain_kernel_for(int kind, bool w_in_smem, bool cluster) {
 // warps as fit instead of packing many chains per SM.
 int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, StreamArgs sa,
                const std::vector<int64_t> *delta_off, bool persistent, int latency_mode = 0) {
+    c->chains_fresh = false;
     LaunchClass cls[kTiers];
     launch_classes(c, cls);
     if (latency_mode) {
@@ -852,6 +855,79 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
         fprintf(stderr, " total=%.0f\n", tot);
     }
 #endif
+    return DICEGP_OK;
+}
+
+// Fresh single-time-point chains that never test convergence (the pre-runs of get_psi): one warp
+// per chain (dicegp_prerun.cuh).  `fast` / `rest`: the chains this path takes / leaves to run_chains.
+bool prerun_eligible(const dicegp_ctx *c, int chain, size_t *smem_bytes) {
+    const dicegp_chain_desc &d = c->hdesc[chain];
+    const int C = c->hC[d.gene];
+    if (d.Tc != 1 || C < 2 || C > DG_MAXC || d.prop_factor_off < 0) return false;
+    if (d.initial < d.M || d.M > (1 << c->hpshift[chain])) return false;       // no check step, one trace page
+    const size_t wd = (size_t)chain_wbytes(c, chain) / sizeof(double);
+    const size_t bytes = (wd + (size_t)dg::dg_prerun_scratch(C)) * sizeof(double);
+    if (bytes > 110 * 1024) return false;                                      // at least two chains per SM
+    *smem_bytes = bytes;
+    return true;
+}
+
+int run_prerun_warps(dicegp_ctx *c, const std::vector<int32_t> &ids, uint64_t seed) {
+    c->chains_fresh = false;
+    std::vector<int32_t> by_kind[kKinds];
+    for (int32_t id : ids) by_kind[kind_of(c->hC[c->hdesc[id].gene])].push_back(id);
+    std::vector<int32_t> flat;
+    size_t base[kKinds + 1];
+    for (int k = 0; k < kKinds; ++k) { base[k] = flat.size(); flat.insert(flat.end(), by_kind[k].begin(), by_kind[k].end()); }
+    base[kKinds] = flat.size();
+    DG_CUDA(c, c->dids.resize(flat.size()));
+    DG_CUDA(c, cudaMemcpyAsync(c->dids.p, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    DG_CUDA(c, c->dqueue.resize(kGroups));
+    DG_CUDA(c, cudaMemsetAsync(c->dqueue.p, 0, kGroups * sizeof(int), c->stream));
+    typedef void (*prerun_kernel_t)(GeneTab, ChainTab, uint64_t, const int32_t *, int, int *, int);
+    static const prerun_kernel_t kernels[kKinds] = {
+        dicegp_prerun_kernel<0>, dicegp_prerun_kernel<2>, dicegp_prerun_kernel<3>, dicegp_prerun_kernel<4>,
+        dicegp_prerun_kernel<5>, dicegp_prerun_kernel<6>, dicegp_prerun_kernel<7>, dicegp_prerun_kernel<8>};
+    for (int k = 0; k < kKinds; ++k)
+        DG_CUDA(c, cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    GeneTab gt = make_gene_tab(c);
+    ChainTab ct = make_chain_tab(c);
+    DG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    DG_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+    int64_t launches = 0, steps = 0, evals = 0;
+    for (int k = kKinds - 1; k >= 0; --k) {                 // many isoforms first: fewest chains per SM, longest steps
+        const int n_ids = (int)by_kind[k].size();
+        if (n_ids == 0) continue;
+        size_t wd = 0;
+        int maxC = 2;
+        for (int32_t id : by_kind[k]) {
+            wd = std::max(wd, (size_t)chain_wbytes(c, id) / sizeof(double));
+            maxC = std::max(maxC, c->hC[c->hdesc[id].gene]);
+            steps += c->hdesc[id].M;
+            evals += (int64_t)(c->hdesc[id].M + 1) * chain_reads(c, id);      // + the start value
+        }
+        wd = (wd + 1) & ~(size_t)1;
+        const size_t smem = (wd + (size_t)dg::dg_prerun_scratch(maxC)) * sizeof(double);
+        const int bps = (int)std::min<size_t>(32, 233472 / (smem + 1024));
+        const int grid = std::min(n_ids, c->sm_count * std::max(bps, 1));
+        cudaStream_t st = c->class_stream[k];
+        DG_CUDA(c, cudaStreamWaitEvent(st, c->ev_fork, 0));
+        kernels[k]<<<grid, 32, smem, st>>>(gt, ct, seed, c->dids.p + base[k], n_ids, c->dqueue.p + k, (int)wd);
+        DG_CUDA(c, cudaGetLastError());
+        ++launches;
+        ++c->total_launches;
+        DG_CUDA(c, cudaEventRecord(c->ev_join[k], st));
+        DG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[k], 0));
+    }
+    DG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    DG_CUDA(c, cudaStreamSynchronize(c->stream));
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return c->cuda_fail(e, "pre-run kernel");
+    }
+    float ms = 0.f;
+    DG_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_ms = ms; c->last_launches = launches; c->last_evals = evals; c->last_steps = steps;
     return DICEGP_OK;
 }
 
@@ -1106,6 +1182,7 @@ static int install_chains(dicegp_ctx *c, int32_t n, const dicegp_chain_desc *des
     DG_CUDA(c, cudaStreamSynchronize(s));
     c->have_stream_id = false;
     c->n_chains = n;
+    c->chains_fresh = true;
     return DICEGP_OK;
 }
 
@@ -1216,9 +1293,35 @@ int dicegp_run_device_stream(dicegp_ctx *c, uint64_t seed, const int64_t *stream
     } else {
         c->have_stream_id = false;
     }
-    std::vector<int32_t> ids(c->n_chains);
+    std::vector<int32_t> ids;
+    double fast_ms = 0.0;
+    int64_t fast_launches = 0, fast_evals = 0, fast_steps = 0;
+    {
+        // fresh single-time-point chains without a convergence check (get_psi's pre-runs) take the
+        // warp-per-chain kernel; DICEGP_PRERUN_KERNEL=0 sends them through the general one
+        const char *e = getenv("DICEGP_PRERUN_KERNEL");
+        const bool use_fast = c->chains_fresh && !(e && e[0] == '0');
+        std::vector<int32_t> fast;
+        for (int i = 0; i < c->n_chains; ++i) {
+            size_t bytes = 0;
+            if (use_fast && prerun_eligible(c, i, &bytes)) fast.push_back(i);
+            else ids.push_back(i);
+        }
+        if (!fast.empty()) {
+            int rc = run_prerun_warps(c, fast, seed);
+            if (rc != DICEGP_OK) return rc;
+            fast_ms = c->last_ms; fast_launches = c->last_launches; fast_evals = c->last_evals; fast_steps = c->last_steps;
+            if (getenv("DICEGP_VERBOSE"))
+                fprintf(stderr, "[dicegp] pre-run kernel: %.1f ms, %lld steps, %zu chains\n", fast_ms, (long long)fast_steps, fast.size());
+            if (ids.empty()) return DICEGP_OK;
+        }
+    }
+    struct AddFast {                                             // the general path's stats + the fast path's
+        dicegp_ctx *c; double ms; int64_t l, e, s;
+        ~AddFast() { c->last_ms += ms; c->last_launches += l; c->last_evals += e; c->last_steps += s; }
+    } add_fast{c, fast_ms, fast_launches, fast_evals, fast_steps};
     int max_M = 0;
-    for (int i = 0; i < c->n_chains; ++i) { ids[i] = i; max_M = std::max(max_M, c->hdesc[i].M); }
+    for (int32_t i : ids) max_M = std::max(max_M, c->hdesc[i].M);
     StreamArgs sa;
     memset(&sa, 0, sizeof sa);
     sa.mode = 1;

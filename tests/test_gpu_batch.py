@@ -184,3 +184,26 @@ def test_human_scale_batch_is_self_consistent(sampler):
                     z = orc.geweke_z(Psi[:r.m, c, t])
                     assert z is not None and z <= 2
     assert n_conv > 0
+
+
+def test_warp_per_chain_prerun_kernel_equals_general_kernel(sampler, monkeypatch):
+    """The pre-runs (single time point, no convergence check) take the warp-per-chain kernel;
+    DICEGP_PRERUN_KERNEL=0 sends them through the general chain kernel.  Same stream, same
+    arithmetic per step: identical accept decisions, hence bit-identical jump variances and an
+    identical main run.  Includes odd read counts, a 12-isoform gene (run-time isoform count) and
+    ragged human-scale genes (those too large for shared memory fall back to the general kernel)."""
+    genes = [synth.gene_W("timeseries", g, reads=r, T=3) for g, r in zip(range(100, 112), [999, 1000, 1, 37, 501] * 3)]
+    genes += [synth.gene_W("timeseries", 112, reads=333, T=3, C=12)]
+    genes += [synth.gene_W("human", g)[0][:3] and (synth.gene_W("human", g)[0][:3], synth.gene_W("human", g)[1][:3])
+              for g in (1, 2, 3)]
+    packed = pack_genes(genes)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DICEGP_PRERUN_KERNEL", mode)
+        res = sampler.run(packed, M=1300, initial=1000, gap=100, seed=17)
+        out[mode] = (res.var.copy(), res.m.copy(), res.cnt.copy(), res.psi_mean.copy())
+        n_launch = sampler.stats["prerun_launches"]
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert np.array_equal(out["0"][1], out["1"][1]) and np.array_equal(out["0"][2], out["1"][2])
+    assert np.array_equal(out["0"][3], out["1"][3])
+    assert n_launch > 0
