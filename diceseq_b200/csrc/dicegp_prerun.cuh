@@ -27,13 +27,15 @@ __host__ __device__ inline int dg_prerun_scratch(int C) {
 struct PrerunEval { double lik, prior; };
 
 // likelihood of the state whose f sits in fv[0..C): sum_n log(sum_k W[n,k] f[k])  (model_GP.py:338-345).
-// KC = compile-time isoform count (0: run-time C).  Four read pairs per lane and iteration: the
-// dot products and the four running products are independent dependency chains (one warp has
-// nothing else to hide the 23-cycle fp64 latency with).
+// KC = compile-time isoform count (0: run-time C).  Eight read pairs per lane and iteration: their
+// dot products and the four running products are independent dependency chains (a chain's single
+// warp has nothing else to hide the shared-memory and the 23-cycle fp64 latency with; registers
+// are plentiful at 3-14 warps per SM).
 template <int KC>
 __device__ __forceinline__ double dg_prerun_lik(const double2 *W2, const double *fv, int C_rt, int npairs, int n, int lane) {
     const int C = KC > 0 ? KC : C_rt;
     constexpr int FR = KC > 0 ? KC : 1;
+    constexpr int U = 8;                                  // read pairs per lane and iteration
     double fr[FR];
     if (KC > 0) {
 #pragma unroll
@@ -43,27 +45,26 @@ __device__ __forceinline__ double dg_prerun_lik(const double2 *W2, const double 
     int ee = 0, it = 0;
     unsigned bad = 0u;
     const int last = npairs - 1;
-    for (int p0 = lane; p0 < npairs; p0 += 128, ++it) {
-        double x0[4] = {0.0, 0.0, 0.0, 0.0}, x1[4] = {0.0, 0.0, 0.0, 0.0};
-        int pc[4];
+    for (int p0 = lane; p0 < npairs; p0 += 32 * U, ++it) {
+        double x0[U], x1[U];
+        int pc[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) pc[u] = min(p0 + 32 * u, last);
+        for (int u = 0; u < U; ++u) { pc[u] = min(p0 + 32 * u, last); x0[u] = 0.0; x1[u] = 0.0; }
+        if (KC > 0) {
 #pragma unroll
-        for (int k = 0; k < (KC > 0 ? KC : 1); ++k) {
-            if (KC > 0) {
+            for (int k = 0; k < FR; ++k) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const double2 w = W2[(size_t)k * npairs + pc[u]];
                     x0[u] = fma(w.x, fr[k], x0[u]);
                     x1[u] = fma(w.y, fr[k], x1[u]);
                 }
             }
-        }
-        if (KC == 0) {
+        } else {
             for (int k = 0; k < C; ++k) {
                 const double f = fv[k];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const double2 w = W2[(size_t)k * npairs + pc[u]];
                     x0[u] = fma(w.x, f, x0[u]);
                     x1[u] = fma(w.y, f, x1[u]);
@@ -71,7 +72,7 @@ __device__ __forceinline__ double dg_prerun_lik(const double2 *W2, const double 
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int p = p0 + 32 * u;
             const double a0 = p < npairs ? x0[u] : 1.0;
             const double a1 = (p < npairs && 2 * p + 1 < n) ? x1[u] : 1.0;   // the pad slot of an odd read count
@@ -81,9 +82,9 @@ __device__ __forceinline__ double dg_prerun_lik(const double2 *W2, const double 
             bad |= ((unsigned)(h - 0x00100000) >= 0x7fe00000u) ? 1u : 0u;
             bad |= (unsigned)sg >> 31;
             ee += (h >> 20) - 1023;
-            mm[u] *= __hiloint2double((h & 0x000fffff) | 0x3ff00000, __double2loint(pr2));
+            mm[u & 3] *= __hiloint2double((h & 0x000fffff) | 0x3ff00000, __double2loint(pr2));
         }
-        if ((it & 63) == 63) {                                               // keep the running products in range
+        if ((it & 31) == 31) {                                               // keep the running products in range
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int g = __double2hiint(mm[u]);

@@ -194,8 +194,9 @@ def test_warp_per_chain_prerun_kernel_equals_general_kernel(sampler, monkeypatch
     ragged human-scale genes (those too large for shared memory fall back to the general kernel)."""
     genes = [synth.gene_W("timeseries", g, reads=r, T=3) for g, r in zip(range(100, 112), [999, 1000, 1, 37, 501] * 3)]
     genes += [synth.gene_W("timeseries", 112, reads=333, T=3, C=12)]
-    genes += [synth.gene_W("human", g)[0][:3] and (synth.gene_W("human", g)[0][:3], synth.gene_W("human", g)[1][:3])
-              for g in (1, 2, 3)]
+    for g in (0, 1, 2, 3):                      # gene 0: 642 / 9948 / 6272 reads x 6 isoforms -> two chains fall back
+        W, lens = synth.gene_W("human", g)
+        genes.append((W[:3], lens[:3]))
     packed = pack_genes(genes)
     out = {}
     for mode in ("0", "1"):
