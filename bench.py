@@ -210,7 +210,7 @@ def run_reference(args, wl):
                                    "reference's per-step inv/det/svd cost" % (n_genes, cores)},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_json_line(line)
 
 
 # ----------------------------------------------------------------------------------------
@@ -406,13 +406,36 @@ def run_ours(args, wl):
     if cpu_line is not None:
         line["cpu_baseline"] = cpu_line
     if rank == 0:
-        print(json.dumps(line))
+        emit_json_line(line)
     pipe.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result.  Libraries write there too (NCCL prints its
+    version banner on the first communicator), so everything else that targets fd 1 is sent to
+    stderr and the result line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
