@@ -866,7 +866,8 @@ bool prerun_eligible(const dicegp_ctx *c, int chain, size_t *smem_bytes) {
     if (d.Tc != 1 || C < 2 || C > DG_MAXC || d.prop_factor_off < 0) return false;
     if (d.initial < d.M || d.M > (1 << c->hpshift[chain])) return false;       // no check step, one trace page
     const size_t wd = (size_t)chain_wbytes(c, chain) / sizeof(double);
-    const size_t bytes = (wd + (size_t)dg::dg_prerun_scratch(C)) * sizeof(double);
+    // (the run-time-C group shares one launch: its scratch is sized for the largest isoform count)
+    const size_t bytes = (wd + (size_t)dg::dg_prerun_scratch(kind_of(C) == 0 ? DG_MAXC : C)) * sizeof(double);
     if (bytes > 110 * 1024) return false;                                      // at least two chains per SM
     *smem_bytes = bytes;
     return true;
@@ -907,7 +908,7 @@ int run_prerun_warps(dicegp_ctx *c, const std::vector<int32_t> &ids, uint64_t se
             evals += (int64_t)(c->hdesc[id].M + 1) * chain_reads(c, id);      // + the start value
         }
         wd = (wd + 1) & ~(size_t)1;
-        const size_t smem = (wd + (size_t)dg::dg_prerun_scratch(maxC)) * sizeof(double);
+        const size_t smem = (wd + (size_t)dg::dg_prerun_scratch(k == 0 ? DG_MAXC : maxC)) * sizeof(double);
         const int bps = (int)std::min<size_t>(32, 233472 / (smem + 1024));
         const int grid = std::min(n_ids, c->sm_count * std::max(bps, 1));
         cudaStream_t st = c->class_stream[k];
