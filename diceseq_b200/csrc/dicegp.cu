@@ -858,13 +858,12 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     return DICEGP_OK;
 }
 
-// Fresh single-time-point chains that never test convergence (the pre-runs of get_psi): one warp
-// per chain (dicegp_prerun.cuh).  `fast` / `rest`: the chains this path takes / leaves to run_chains.
+// Single-time-point chains (the pre-runs of get_psi, static mode) whose W fits shared memory: one
+// warp per chain (dicegp_prerun.cuh), advanced by up to n_steps.
 bool prerun_eligible(const dicegp_ctx *c, int chain, size_t *smem_bytes) {
     const dicegp_chain_desc &d = c->hdesc[chain];
     const int C = c->hC[d.gene];
     if (d.Tc != 1 || C < 2 || C > DG_MAXC || d.prop_factor_off < 0) return false;
-    if (d.initial < d.M || d.M > (1 << c->hpshift[chain])) return false;       // no check step, one trace page
     const size_t wd = (size_t)chain_wbytes(c, chain) / sizeof(double);
     // (the run-time-C group shares one launch: its scratch is sized for the largest isoform count)
     const size_t bytes = (wd + (size_t)dg::dg_prerun_scratch(kind_of(C) == 0 ? DG_MAXC : C)) * sizeof(double);
@@ -873,8 +872,10 @@ bool prerun_eligible(const dicegp_ctx *c, int chain, size_t *smem_bytes) {
     return true;
 }
 
-int run_prerun_warps(dicegp_ctx *c, const std::vector<int32_t> &ids, uint64_t seed) {
+int run_prerun_warps(dicegp_ctx *c, const std::vector<int32_t> &ids, uint64_t seed, int n_steps) {
     c->chains_fresh = false;
+    c->hm_next_before.resize(c->n_chains);
+    DG_CUDA(c, cudaMemcpyAsync(c->hm_next_before.data(), c->cm_next.p, c->n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     std::vector<int32_t> by_kind[kKinds];
     for (int32_t id : ids) by_kind[kind_of(c->hC[c->hdesc[id].gene])].push_back(id);
     std::vector<int32_t> flat;
@@ -885,7 +886,7 @@ int run_prerun_warps(dicegp_ctx *c, const std::vector<int32_t> &ids, uint64_t se
     DG_CUDA(c, cudaMemcpyAsync(c->dids.p, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     DG_CUDA(c, c->dqueue.resize(kGroups));
     DG_CUDA(c, cudaMemsetAsync(c->dqueue.p, 0, kGroups * sizeof(int), c->stream));
-    typedef void (*prerun_kernel_t)(GeneTab, ChainTab, uint64_t, const int32_t *, int, int *, int);
+    typedef void (*prerun_kernel_t)(GeneTab, ChainTab, uint64_t, const int32_t *, int, int *, int, int);
     static const prerun_kernel_t kernels[kKinds] = {
         dicegp_prerun_kernel<0>, dicegp_prerun_kernel<2>, dicegp_prerun_kernel<3>, dicegp_prerun_kernel<4>,
         dicegp_prerun_kernel<5>, dicegp_prerun_kernel<6>, dicegp_prerun_kernel<7>, dicegp_prerun_kernel<8>};
@@ -904,8 +905,6 @@ int run_prerun_warps(dicegp_ctx *c, const std::vector<int32_t> &ids, uint64_t se
         for (int32_t id : by_kind[k]) {
             wd = std::max(wd, (size_t)chain_wbytes(c, id) / sizeof(double));
             maxC = std::max(maxC, c->hC[c->hdesc[id].gene]);
-            steps += c->hdesc[id].M;
-            evals += (int64_t)(c->hdesc[id].M + 1) * chain_reads(c, id);      // + the start value
         }
         wd = (wd + 1) & ~(size_t)1;
         const size_t smem = (wd + (size_t)dg::dg_prerun_scratch(k == 0 ? DG_MAXC : maxC)) * sizeof(double);
@@ -913,7 +912,7 @@ int run_prerun_warps(dicegp_ctx *c, const std::vector<int32_t> &ids, uint64_t se
         const int grid = std::min(n_ids, c->sm_count * std::max(bps, 1));
         cudaStream_t st = c->class_stream[k];
         DG_CUDA(c, cudaStreamWaitEvent(st, c->ev_fork, 0));
-        kernels[k]<<<grid, 32, smem, st>>>(gt, ct, seed, c->dids.p + base[k], n_ids, c->dqueue.p + k, (int)wd);
+        kernels[k]<<<grid, 32, smem, st>>>(gt, ct, seed, c->dids.p + base[k], n_ids, c->dqueue.p + k, (int)wd, n_steps);
         DG_CUDA(c, cudaGetLastError());
         ++launches;
         ++c->total_launches;
@@ -928,6 +927,14 @@ int run_prerun_warps(dicegp_ctx *c, const std::vector<int32_t> &ids, uint64_t se
     }
     float ms = 0.f;
     DG_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    std::vector<int32_t> after(c->n_chains);
+    DG_CUDA(c, cudaMemcpy(after.data(), c->cm_next.p, c->n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int32_t id : ids) {
+        const int64_t ds = (int64_t)after[id] - c->hm_next_before[id];
+        const int64_t init_eval = (c->hm_next_before[id] == 0 && after[id] > 0) ? 1 : 0;     // the start value
+        steps += ds;
+        evals += (ds + init_eval) * chain_reads(c, id);
+    }
     c->last_ms = ms; c->last_launches = launches; c->last_evals = evals; c->last_steps = steps;
     return DICEGP_OK;
 }
@@ -1298,10 +1305,12 @@ int dicegp_run_device_stream(dicegp_ctx *c, uint64_t seed, const int64_t *stream
     double fast_ms = 0.0;
     int64_t fast_launches = 0, fast_evals = 0, fast_steps = 0;
     {
-        // fresh single-time-point chains without a convergence check (get_psi's pre-runs) take the
-        // warp-per-chain kernel; DICEGP_PRERUN_KERNEL=0 sends them through the general one
+        // single-time-point chains (get_psi's pre-runs, static mode) whose W fits shared memory take the
+        // warp-per-chain kernel and run to their end in one launch (a step costs them ~2.5 us, so
+        // even a chain that uses all M steps is short); DICEGP_PRERUN_KERNEL=0 sends them through
+        // the general kernel
         const char *e = getenv("DICEGP_PRERUN_KERNEL");
-        const bool use_fast = c->chains_fresh && !(e && e[0] == '0');
+        const bool use_fast = !(e && e[0] == '0');
         std::vector<int32_t> fast;
         for (int i = 0; i < c->n_chains; ++i) {
             size_t bytes = 0;
@@ -1309,11 +1318,13 @@ int dicegp_run_device_stream(dicegp_ctx *c, uint64_t seed, const int64_t *stream
             else ids.push_back(i);
         }
         if (!fast.empty()) {
-            int rc = run_prerun_warps(c, fast, seed);
+            int fast_M = 0;
+            for (int32_t i : fast) fast_M = std::max(fast_M, c->hdesc[i].M);
+            int rc = run_prerun_warps(c, fast, seed, fast_M);
             if (rc != DICEGP_OK) return rc;
             fast_ms = c->last_ms; fast_launches = c->last_launches; fast_evals = c->last_evals; fast_steps = c->last_steps;
             if (getenv("DICEGP_VERBOSE"))
-                fprintf(stderr, "[dicegp] pre-run kernel: %.1f ms, %lld steps, %zu chains\n", fast_ms, (long long)fast_steps, fast.size());
+                fprintf(stderr, "[dicegp] warp-per-chain kernel: %.1f ms, %lld steps, %zu chains\n", fast_ms, (long long)fast_steps, fast.size());
             if (ids.empty()) return DICEGP_OK;
         }
     }

@@ -1,5 +1,6 @@
-// dicegp_prerun.cuh -- single-time-point chains without a convergence check: the pre-runs
-// of get_psi (diceseq/utils/run_utils.py:107-114: T chains per gene, M = 100, initial = 100).
+// dicegp_prerun.cuh -- single-time-point chains, one WARP per chain: the pre-runs of get_psi
+// (diceseq/utils/run_utils.py:107-114: T chains per gene, M = 100, no convergence check) and
+// the chains of static mode (one time point: `diceseq` on a single sample).
 //
 // The general chain kernel gives such a chain a whole thread block whose warps take turns
 // (state warp -> likelihood warps -> decision), and the registers of those mostly idle warps
@@ -7,9 +8,11 @@
 // one chain and one block: lane c owns isoform c, the 1000 reads of the time point are split
 // over the 32 lanes, there is no block barrier at all, and an SM holds as many chains as their
 // W fits shared memory (3 with 8 isoforms ... 14 with 2).  Same arithmetic per step as
-// dg::run_chain with Tc = 1 (model_GP.py:312-366): same Philox stream, same softmax / prior /
+// dg::run_chain with Tc = 1 (model_GP.py:312-391): same Philox stream, same softmax / prior /
 // accept expressions, likelihood as a (mantissa product, exponent sum) over read pairs with the
-// real-log path for anything that is not a positive normal number.
+// real-log path for anything that is not a positive normal number, the same paged trace, the
+// same incremental Geweke rule and the same saved state -- a chain can be advanced by either
+// kernel in turn.
 #pragma once
 #include "dicegp_kernels.cuh"
 
@@ -18,10 +21,10 @@ namespace dg {
 #define DG_PR_BATCH 32          // stream steps produced at a time (all lanes busy)
 
 // shared memory of one pre-run chain, in doubles, after its W: normals/increments and Q terms of a
-// batch (2 x 32 x ZP), log u and Q per step (2 x 32), per-isoform scratch (7 x CP)
+// batch (2 x 32 x ZP), log u and Q per step (2 x 32), per-isoform scratch (7 x CP), Geweke scratch (64)
 __host__ __device__ inline int dg_prerun_zp(int C) { return 2 * (C >> 1) > 2 ? 2 * (C >> 1) : 2; }
 __host__ __device__ inline int dg_prerun_scratch(int C) {
-    return 2 * DG_PR_BATCH * dg_prerun_zp(C) + 2 * DG_PR_BATCH + 7 * ((C + 1) & ~1);
+    return 2 * DG_PR_BATCH * dg_prerun_zp(C) + 2 * DG_PR_BATCH + 7 * ((C + 1) & ~1) + 2 * DG_GW_COLS;
 }
 
 struct PrerunEval { double lik, prior; };
@@ -139,12 +142,12 @@ __device__ __forceinline__ double dg_prerun_lik(const double2 *W2, const double 
 
 }  // namespace dg
 
-// One warp (= one block) per chain; persistent blocks pull chains from `queue`.
-// w_doubles: doubles reserved for W at the start of the dynamic shared memory.
+// One warp (= one block) per chain; persistent blocks pull chains from `queue` and advance them by
+// up to n_steps.  w_doubles: doubles reserved for W at the start of the dynamic shared memory.
 template <int KC>
 __global__ void __launch_bounds__(32)
 dicegp_prerun_kernel(GeneTab gt, ChainTab ct, uint64_t seed, const int32_t *__restrict__ ids, int n_ids, int *queue,
-                     int w_doubles) {
+                     int w_doubles, int n_steps) {
     extern __shared__ __align__(16) double dg_pr_smem[];
     const int lane = threadIdx.x;
     constexpr unsigned FULL = 0xffffffffu;
@@ -154,7 +157,9 @@ dicegp_prerun_kernel(GeneTab gt, ChainTab ct, uint64_t seed, const int32_t *__re
         slot = __shfl_sync(FULL, slot, 0);
         if (slot >= n_ids) break;
         const int chain = ids[slot];
+        if (ct.state[chain] != 0) continue;                  // finished earlier
         const int g = ct.gene[chain], t = ct.t0[chain], T = gt.T, C = KC > 0 ? KC : gt.C[g], M = ct.M[chain];
+        const int initial = ct.initial[chain], gap = ct.gap[chain];
         const int32_t *roff = gt.roff + (size_t)g * (T + 1) + t;
         const int npairs = (roff[1] - roff[0]) >> 1, n = gt.ncnt[(size_t)g * T + t];
         const double2 *Wg = reinterpret_cast<const double2 *>(gt.W + gt.woff[g] + (size_t)C * roff[0]);
@@ -165,7 +170,7 @@ dicegp_prerun_kernel(GeneTab gt, ChainTab ct, uint64_t seed, const int32_t *__re
         double *lur = qt + DG_PR_BATCH * ZP;                 // [32] log u
         double *Qr = lur + DG_PR_BATCH;                      // [32] Q
         double *ev = Qr + DG_PR_BATCH, *gv = ev + CP, *fv = gv + CP, *pv = fv + CP;
-        double *sqs = pv + CP, *ijs = sqs + CP, *jcon = ijs + CP;
+        double *sqs = pv + CP, *ijs = sqs + CP, *jcon = ijs + CP, *gw = jcon + CP;
 
         __syncwarp();                                        // the previous chain is done with the shared memory
         for (int i = lane; i < C * npairs; i += 32) W2[i] = Wg[i];
@@ -182,10 +187,25 @@ dicegp_prerun_kernel(GeneTab gt, ChainTab ct, uint64_t seed, const int32_t *__re
         const double len_own = own ? gt.len[gt.lenoff[g] + (size_t)t * C + lane] : 0.0;
         const int64_t sid = ct.stream_id ? ct.stream_id[chain] : (int64_t)chain;
         const int rowlen = 2 * C + 2;
-        double *rows = ct.trace + ct.ptab[ct.ptab_off[chain]];          // first (and only) page
-        double y_now = (own && ct.y0_off[chain] >= 0) ? pool[ct.y0_off[chain] + lane] : 0.0;   // Y_now = Ymean (:275)
-        double psi_now = 0.0, P_now = 0.0, L_now = 0.0;
-        int cnt = 0, flags = 0;
+        int64_t *ptab = ct.ptab + ct.ptab_off[chain];
+        const int pshift = ct.pshift[chain], pmask = (1 << pshift) - 1;
+        TraceView tv;
+        tv.pool = ct.trace; tv.tab = ptab; tv.shift = pshift; tv.rowlen = rowlen;
+        double *st = ct.st + ct.st_off[chain];
+        double *gst = st + rowlen;                                        // running Geweke sums
+        int m = ct.m_next[chain];
+        const int m_end = (m + n_steps < M) ? m + n_steps : M;
+        double y_now = 0.0, psi_now = 0.0, P_now = 0.0, L_now = 0.0;
+        int cnt = 0, flags = 0, state = 0, m_ret = 0;
+        if (m == 0) {
+            if (own && ct.y0_off[chain] >= 0) y_now = pool[ct.y0_off[chain] + lane];   // Y_now = Ymean (:275)
+            if (lane < 4) gst[lane] = 0.0;
+        } else {                                                          // resume (saved by either kernel)
+            if (own) { y_now = st[lane]; psi_now = st[C + lane]; }
+            P_now = st[2 * C]; L_now = st[2 * C + 1];
+            cnt = ct.cnt[chain]; flags = ct.flags[chain];
+        }
+        long long page_cur = -1;
         __syncwarp();
 
         // candidate y (lane c) -> psi (lane c), prior, likelihood            (model_GP.py:332-345)
@@ -208,7 +228,7 @@ dicegp_prerun_kernel(GeneTab gt, ChainTab ct, uint64_t seed, const int32_t *__re
             return r;
         };
 
-        {   // start value (:275-292)
+        if (m == 0) {   // start value (:275-292)
             double psi = 0.0;
             const dg::PrerunEval r = evaluate(y_now, psi);
             psi_now = psi;
@@ -216,8 +236,8 @@ dicegp_prerun_kernel(GeneTab gt, ChainTab ct, uint64_t seed, const int32_t *__re
             P_now = r.prior + r.lik;
             if (!isfinite(P_now)) flags |= 1;
         }
-        for (int m0 = 0; m0 < M; m0 += DG_PR_BATCH) {
-            const int nb = min(DG_PR_BATCH, M - m0), npair = C >> 1;
+        for (int m0 = m; m0 < m_end && state == 0; m0 += DG_PR_BATCH) {
+            const int nb = min(DG_PR_BATCH, m_end - m0), npair = C >> 1;
             // ---- the stream of nb steps: normals -> increments, log u, proposal log-density Q ----
             for (int q = lane; q < nb * npair; q += 32) {
                 const int s = q / npair, i = q - s * npair;
@@ -244,7 +264,13 @@ dicegp_prerun_kernel(GeneTab gt, ChainTab ct, uint64_t seed, const int32_t *__re
             __syncwarp();
             // ---- the steps ----
             for (int s = 0; s < nb; ++s) {
-                const int m = m0 + s;
+                // trace page of row m (first touch allocates from the pool)
+                if (page_cur < 0 || (m & pmask) == 0) {
+                    long long pg = 0;
+                    if (lane == 0) pg = dg::trace_page(ptab, m, pshift, rowlen, ct.pool_head, ct.pool_cap);
+                    page_cur = __shfl_sync(FULL, pg, 0);
+                    if (page_cur < 0) { state = dg::DICEGP_CHAIN_NOMEM_; m_ret = m - 1; break; }
+                }
                 const double y_try = free_ ? zr[s * ZP + lane] + y_now : 0.0; // (:329; Y_try[C-1] stays 0)
                 double psi_try = 0.0;
                 const dg::PrerunEval r = evaluate(y_try, psi_try);
@@ -254,22 +280,33 @@ dicegp_prerun_kernel(GeneTab gt, ChainTab ct, uint64_t seed, const int32_t *__re
                 const bool acc = (a >= 0.0) || (lu < a);                      // u < exp(min(a, 0)); NaN a: both false
                 if (!isfinite(P_try)) flags |= 1;
                 if (acc) { ++cnt; P_now = P_try; L_now = r.lik; y_now = y_try; psi_now = psi_try; }
-                double *row = rows + (size_t)m * rowlen;                      // (:362-366)
+                double *row = ct.trace + page_cur + (size_t)(m & pmask) * rowlen;   // (:362-366)
                 if (own) { row[lane] = psi_now; row[C + lane] = y_now; }
                 if (lane == 0) { row[2 * C] = P_now; row[2 * C + 1] = L_now; }
+                const int mlast = m;
+                ++m;
+                // convergence diagnostics (:369-391) over rows [0, mlast)
+                if (mlast >= initial && (mlast % gap) == 0) {
+                    __syncwarp();                                             // the rows are visible to the warp
+                    if (dg::geweke_converged(gw, gst, C - 1, 1, 0, lane, tv, mlast)) {
+                        state = dg::DICEGP_CHAIN_CONVERGED_;
+                        m_ret = mlast;
+                        break;
+                    }
+                }
             }
         }
-        // ---- final state, as dg::run_chain leaves it ----
-        double *st = ct.st + ct.st_off[chain];
+        if (state == 0 && m >= M) { state = dg::DICEGP_CHAIN_EXHAUSTED_; m_ret = M - 1; }
+        // ---- save state, as dg::run_chain does ----
+        __syncwarp();
         if (own) { st[lane] = y_now; st[C + lane] = psi_now; }
-        if (lane < 4) st[rowlen + lane] = 0.0;                                // Geweke window sums: never used
         if (lane == 0) {
             st[2 * C] = P_now; st[2 * C + 1] = L_now;
-            ct.m_next[chain] = M;
+            ct.m_next[chain] = m;
             ct.cnt[chain] = cnt;
             ct.flags[chain] = flags;
-            ct.m_ret[chain] = M - 1;
-            ct.state[chain] = dg::DICEGP_CHAIN_EXHAUSTED_;
+            ct.m_ret[chain] = m_ret;
+            ct.state[chain] = state;
         }
     }
 }

@@ -208,3 +208,25 @@ def test_warp_per_chain_prerun_kernel_equals_general_kernel(sampler, monkeypatch
     assert np.array_equal(out["0"][1], out["1"][1]) and np.array_equal(out["0"][2], out["1"][2])
     assert np.array_equal(out["0"][3], out["1"][3])
     assert n_launch > 0
+
+
+def test_warp_per_chain_kernel_runs_static_mode_like_the_general_kernel(sampler, monkeypatch):
+    """Static mode (one time point): the joint chains are single-time-point chains too and take the
+    warp-per-chain kernel, with convergence checks and trace pages growing on the device.  Against
+    the general kernel (DICEGP_PRERUN_KERNEL=0): same m, cnt and Y / Psi traces bit for bit,
+    Pro / Lik within 1e-13 (the likelihood is summed in a different order)."""
+    genes = list(range(200, 216))
+    packed = _batch("static", genes)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DICEGP_PRERUN_KERNEL", mode)
+        res = sampler.run(packed, M=2600, initial=1500, gap=100, seed=23, gene_ids=genes, keep_trace=True)
+        out[mode] = [(r.m, r.cnt, r.state, r.trace) for r in res]
+    long_ones = 0
+    for a, b in zip(out["0"], out["1"]):
+        assert a[:3] == b[:3]
+        assert np.array_equal(a[3][0], b[3][0]) and np.array_equal(a[3][1], b[3][1])
+        for k in (2, 3):
+            assert np.allclose(a[3][k], b[3][k], rtol=1e-13, atol=0)
+        long_ones += a[0] > 1024                      # crossed a trace page
+    assert long_ones > 0
