@@ -452,6 +452,14 @@ struct dicegp_ctx {
     DevBuf<double> cprior, cpool, ctrace, cst;
     bool have_stream_id = false;
     bool chains_fresh = false;           // installed and not advanced yet
+    // host staging of install_chains / set_prerun_chains: kept between calls (a batch installs 80k
+    // pre-run chains and 10k joint chains in turn; fresh multi-MB vectors every time mean mmap /
+    // page-fault churn, seen as sporadic 50 ms stalls)
+    std::vector<int64_t> h_ptab;
+    std::vector<int32_t> h_i32[7];
+    std::vector<int64_t> h_i64[5];
+    std::vector<double> h_prior;
+    std::vector<dicegp_chain_desc> h_desc_tmp;
 
     // run scratch
     DevBuf<int32_t> dids;
@@ -1106,10 +1114,15 @@ static int install_chains(dicegp_ctx *c, int32_t n, const dicegp_chain_desc *des
     c->hptab_off.assign(n, 0);
     c->hpshift.assign(n, 0);
     c->hst_off.assign(n, 0);
-    std::vector<int64_t> ptab;
-    std::vector<int32_t> gene(n), t0(n), Tc(n), M(n), ini(n), gap(n);
-    std::vector<int64_t> kinv(n), pf(n), js(n), jc(n), y0(n);
-    std::vector<double> prior(n);
+    std::vector<int64_t> &ptab = c->h_ptab;
+    ptab.clear();
+    std::vector<int32_t> &gene = c->h_i32[0], &t0 = c->h_i32[1], &Tc = c->h_i32[2], &M = c->h_i32[3], &ini = c->h_i32[4],
+                         &gap = c->h_i32[5];
+    std::vector<int64_t> &kinv = c->h_i64[0], &pf = c->h_i64[1], &js = c->h_i64[2], &jc = c->h_i64[3], &y0 = c->h_i64[4];
+    std::vector<double> &prior = c->h_prior;
+    for (std::vector<int32_t> *v : {&gene, &t0, &Tc, &M, &ini, &gap}) v->resize(n);
+    for (std::vector<int64_t> *v : {&kinv, &pf, &js, &jc, &y0}) v->resize(n);
+    prior.resize(n);
     int64_t tr = 0, st = 0, worst = 0;
     for (int i = 0; i < n; ++i) {
         const dicegp_chain_desc &d = desc[i];
@@ -1582,7 +1595,8 @@ int dicegp_set_prerun_chains(dicegp_ctx *c, double theta1, double var0, int32_t 
     int64_t js_off[DG_MAXC + 1], jc_off[DG_MAXC + 1];
     for (int C = 0; C <= DG_MAXC; ++C) js_off[C] = jc_off[C] = -1;
     const int G = c->G, T = c->T;
-    std::vector<dicegp_chain_desc> desc((size_t)G * T);
+    std::vector<dicegp_chain_desc> &desc = c->h_desc_tmp;
+    desc.resize((size_t)G * T);
     for (int g = 0; g < G; ++g) {
         const int C = c->hC[g];
         if (js_off[C] < 0) {
