@@ -1321,7 +1321,9 @@ int dicegp_run_device_stream(dicegp_ctx *c, uint64_t seed, const int64_t *stream
         // single-time-point chains (get_psi's pre-runs, static mode) whose W fits shared memory take the
         // warp-per-chain kernel and run to their end in one launch (a step costs them ~2.5 us, so
         // even a chain that uses all M steps is short); DICEGP_PRERUN_KERNEL=0 sends them through
-        // the general kernel
+        // the general kernel; =1 forces the warp kernel.  Unset: the warp kernel needs a few chains per
+        // SM to pay (a lone warp per chain is a throughput shape: 400 mixed chains ran 20 % slower
+        // with it than with the general kernel, 10k chains 2.4 x faster)
         const char *e = getenv("DICEGP_PRERUN_KERNEL");
         const bool use_fast = !(e && e[0] == '0');
         std::vector<int32_t> fast;
@@ -1329,6 +1331,11 @@ int dicegp_run_device_stream(dicegp_ctx *c, uint64_t seed, const int64_t *stream
             size_t bytes = 0;
             if (use_fast && prerun_eligible(c, i, &bytes)) fast.push_back(i);
             else ids.push_back(i);
+        }
+        if (!(e && e[0] == '1') && (int)fast.size() < 2 * c->sm_count) {
+            ids.resize(c->n_chains);
+            for (int i = 0; i < c->n_chains; ++i) ids[i] = i;
+            fast.clear();
         }
         if (!fast.empty()) {
             int fast_M = 0;
