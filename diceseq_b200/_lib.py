@@ -25,6 +25,7 @@ SYMBOLS = (
     "dicegp_chain_status", "dicegp_download_trace", "dicegp_posterior_summary",
     "dicegp_last_run_stats", "dicegp_set_trace_budget", "dicegp_set_prerun_chains",
     "dicegp_timer_start", "dicegp_timer_stop", "dicegp_counters", "dicegp_eval_loglik",
+    "dicegp_dump_stream",
 )
 
 
@@ -85,6 +86,8 @@ def load():
     lib.dicegp_timer_start.argtypes = [vp]
     lib.dicegp_timer_stop.argtypes = [vp, pd]
     lib.dicegp_counters.argtypes = [vp, pi64, pi64, pi64]
+    lib.dicegp_eval_loglik.argtypes = [vp, i32, i32, i32, pd, pd]
+    lib.dicegp_dump_stream.argtypes = [vp, i32, C.c_uint64, i64, i32, i32, pd, pd]
     for name in SYMBOLS:
         if name != "dicegp_last_error":
             getattr(lib, name).restype = C.c_int
@@ -222,6 +225,16 @@ class Context:
         self._check(self.lib.dicegp_run_host_stream(
             self._h, ids.size, _p(ids, C.c_int32), int(n_steps), _p(delta, C.c_double),
             _p(doff, C.c_int64), delta.size, _p(u, C.c_double)))
+
+    def dump_stream(self, chain, seed, stream_id, n_steps, step0=0):
+        """(delta (n_steps, C-1, Tc), u (n_steps,)) of the device stream of an installed chain
+        (dicegp_dump_stream): what run_device_stream(seed, stream_id) feeds that chain with."""
+        Cn, Tc, _M = self.chain_shapes[chain]
+        delta = np.empty((n_steps, Cn - 1, Tc))
+        u = np.empty(n_steps)
+        self._check(self.lib.dicegp_dump_stream(self._h, int(chain), C.c_uint64(int(seed)), int(stream_id), int(step0),
+                                                int(n_steps), _p(delta, C.c_double), _p(u, C.c_double)))
+        return delta, u
 
     def run_device_stream(self, seed, stream_id=None):
         sid = _i64(stream_id) if stream_id is not None else None

@@ -97,17 +97,40 @@ __device__ double dg_pw_block(const double *v, int n, size_t stride) {
     for (; i < n; ++i) res += v[i * stride];
     return res;
 }
-// numpy splits n > 128 recursively (n2 = n/2 rounded down to a multiple of 8); walked here
-// with an explicit stack because device recursion needs a run-time stack size.
-__device__ double dg_pw_global(const double *v, int n, size_t stride) {
-    if (n <= 128) return dg_pw_block(v, n, stride);
+// numpy splits n > 128 recursively (n2 = n/2 rounded down to a multiple of 8); walked below with an
+// explicit stack because device recursion needs a run-time stack size.
+// The same pairwise sum over column `col` of trace rows [first, first + n) (any n), optionally of the
+// squared deviations from `mean` (np.var's second pass).
+__device__ double dg_pw_trace_block(const TraceView &tv, int first, int col, int n, bool sq, double mean) {
+    auto v = [&](int i) {
+        const double x = __ldcg(tv.row(first + i) + col);
+        if (!sq) return x;
+        const double e = x - mean;
+        return __dmul_rn(e, e);
+    };
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += v(i);
+        return r;
+    }
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = v(j);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] += v(i + j);
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += v(i);
+    return res;
+}
+__device__ double dg_pw_trace(const TraceView &tv, int first, int col, int n, bool sq, double mean) {
+    if (n <= 128) return dg_pw_trace_block(tv, first, col, n, sq, mean);
     int f_off[32], f_n[32], f_state[32], fs = 0, rs = 0;
     double res[34];
     f_off[0] = 0; f_n[0] = n; f_state[0] = 0; fs = 1;
     while (fs > 0) {
         const int k = fs - 1;
         if (f_n[k] <= 128) {
-            res[rs++] = dg_pw_block(v + (size_t)f_off[k] * stride, f_n[k], stride);
+            res[rs++] = dg_pw_trace_block(tv, first + f_off[k], col, f_n[k], sq, mean);
             --fs;
             continue;
         }
@@ -148,26 +171,26 @@ __global__ void dicegp_prerun_var_kernel(GeneTab gt, ChainTab ct, int G, double 
         const int b = (int)((double)m_ret / 4.0);
         const int n = n_rows - b;
         const int rowlen = 2 * C + 2;                       // Tc == 1
-        // pre-run traces (M = 100 rows) live in one page
-        const double *y = ct.trace + ct.ptab[ct.ptab_off[chain]] + (size_t)b * rowlen + C + c;
+        TraceView tv;                                       // rows through the page table (M may exceed a page)
+        tv.pool = ct.trace; tv.tab = ct.ptab + ct.ptab_off[chain]; tv.shift = ct.pshift[chain]; tv.rowlen = rowlen;
+        auto yv = [&](int i) { return __ldcg(tv.row(b + i) + C + c); };
         double mean, ss;
-        if (C == 2) {
-            mean = dg_pw_global(y, n, rowlen) / (double)n;
-            // pairwise over squared deviations: small n (76), do it through a local copy
+        if (C == 2 && n <= 128) {
+            // a (rows, 1) slice collapses to 1-D: pairwise sums (one block of <= 128 values)
             double d[128];
-            if (n <= 128) {
-                for (int i = 0; i < n; ++i) { double e = y[(size_t)i * rowlen] - mean; d[i] = e * e; }
-                ss = dg_pw_global(d, n, 1);
-            } else {
-                ss = 0.0;
-                for (int i = 0; i < n; ++i) { double e = y[(size_t)i * rowlen] - mean; ss += e * e; }
-            }
+            for (int i = 0; i < n; ++i) d[i] = yv(i);
+            mean = dg_pw_block(d, n, 1) / (double)n;
+            for (int i = 0; i < n; ++i) { const double e = d[i] - mean; d[i] = __dmul_rn(e, e); }   // numpy squares, then adds: no fma
+            ss = dg_pw_block(d, n, 1);
+        } else if (C == 2) {
+            mean = dg_pw_trace(tv, b, C + c, n, false, 0.0) / (double)n;
+            ss = dg_pw_trace(tv, b, C + c, n, true, mean);
         } else {
             double s = 0.0;
-            for (int i = 0; i < n; ++i) s += y[(size_t)i * rowlen];
+            for (int i = 0; i < n; ++i) s += yv(i);
             mean = s / (double)n;
             ss = 0.0;
-            for (int i = 0; i < n; ++i) { double e = y[(size_t)i * rowlen] - mean; ss += e * e; }
+            for (int i = 0; i < n; ++i) { const double e = yv(i) - mean; ss += __dmul_rn(e, e); }
         }
         acc += ss / (double)n;
     }
@@ -182,6 +205,40 @@ __global__ void dicegp_gather_rows_kernel(ChainTab ct, int chain, int rowlen, in
     for (int r = blockIdx.x; r < n; r += gridDim.x) {
         const double *src = tv.row(first + r);
         for (int i = threadIdx.x; i < rowlen; i += blockDim.x) out[(size_t)r * rowlen + i] = __ldcg(src + i);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// The device random stream of one chain, written out instead of consumed: the proposal
+// increments delta[s][c][t] and the uniforms u[s] of steps [step0, step0+n) exactly as the chain
+// kernels form them (dg::produce_stream / dicegp_prerun_kernel: same Philox counters, the same
+// Box-Muller pairing, z @ A_K accumulated j ascending with fma, times sqrt(jump_scale[c])).
+// Test instrument: the dumped stream is replayed through the oracle to step-check the
+// device-stream mode (tests/test_gpu_device_stream.py).  One block; z staged in shared memory.
+// ---------------------------------------------------------------------------------------
+__global__ void dicegp_stream_dump_kernel(GeneTab gt, ChainTab ct, int chain, uint64_t seed, int64_t sid, int step0,
+                                          int n, double *__restrict__ delta_out, double *__restrict__ u_out) {
+    __shared__ double z[DG_MAXCT];
+    const int C = gt.C[ct.gene[chain]], Tc = ct.Tc[chain], CTm = (C - 1) * Tc;
+    const double *pfac = ct.pool + ct.pf_off[chain], *js = ct.pool + ct.js_off[chain];
+    const int npair = (CTm + 1) >> 1;
+    for (int s = 0; s < n; ++s) {
+        const uint32_t step = (uint32_t)(step0 + s);
+        for (int i = threadIdx.x; i < npair; i += blockDim.x) {
+            double z0, z1;
+            dg_normal_pair(seed, sid, step, (uint32_t)i, z0, z1);
+            z[2 * i] = z0;
+            if (2 * i + 1 < CTm) z[2 * i + 1] = z1;
+        }
+        if (threadIdx.x == 0) u_out[s] = dg_uniform(seed, sid, step);
+        __syncthreads();
+        for (int i = threadIdx.x; i < CTm; i += blockDim.x) {
+            const int c = i / Tc, t = i - c * Tc;
+            double a = 0.0;
+            for (int j = 0; j < Tc; ++j) a = fma(z[c * Tc + j], pfac[j * Tc + t], a);
+            delta_out[(size_t)s * CTm + i] = sqrt(js[c]) * a;
+        }
+        __syncthreads();
     }
 }
 
@@ -1399,6 +1456,27 @@ int dicegp_run_device_stream(dicegp_ctx *c, uint64_t seed, const int64_t *stream
     return DICEGP_OK;
 }
 
+int dicegp_dump_stream(dicegp_ctx *c, int32_t chain, uint64_t seed, int64_t stream_id, int32_t step0, int32_t n_steps,
+                       double *delta, double *u) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (chain < 0 || chain >= c->n_chains) return c->fail(DICEGP_ERR_ARG, "dump_stream: chain id out of range");
+    if (step0 < 0 || n_steps <= 0 || !delta || !u) return c->fail(DICEGP_ERR_ARG, "dump_stream: NULL buffer or empty step range");
+    const dicegp_chain_desc &d = c->hdesc[chain];
+    if (d.prop_factor_off < 0) return c->fail(DICEGP_ERR_ARG, "dump_stream: chain without prop_factor");
+    DG_CUDA(c, cudaSetDevice(c->device));
+    const size_t ctm = (size_t)(c->hC[d.gene] - 1) * d.Tc;
+    DG_CUDA(c, c->dgather.resize((size_t)n_steps * (ctm + 1)));
+    double *dd = c->dgather.p, *du = dd + (size_t)n_steps * ctm;
+    dicegp_stream_dump_kernel<<<1, 128, 0, c->stream>>>(make_gene_tab(c), make_chain_tab(c), chain, seed, stream_id, step0,
+                                                        n_steps, dd, du);
+    DG_CUDA(c, cudaGetLastError());
+    ++c->total_launches;
+    if (ctm > 0) DG_CUDA(c, cudaMemcpyAsync(delta, dd, (size_t)n_steps * ctm * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    DG_CUDA(c, cudaMemcpyAsync(u, du, (size_t)n_steps * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    DG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return DICEGP_OK;
+}
+
 int dicegp_eval_loglik(dicegp_ctx *c, int32_t gene, int32_t t0, int32_t Tc, const double *y, double *lik) {
     if (!c) return DICEGP_ERR_ARG;
     if (c->G == 0) return c->fail(DICEGP_ERR_STATE, "eval_loglik: no genes uploaded");
@@ -1461,6 +1539,13 @@ int dicegp_download_trace(dicegp_ctx *c, int32_t chain, int32_t first_row, int32
     if (first_row < 0 || n_rows < 0 || first_row + n_rows > d.M) return c->fail(DICEGP_ERR_ARG, "download_trace: row range outside the trace");
     if (n_rows == 0) return DICEGP_OK;
     DG_CUDA(c, cudaSetDevice(c->device));
+    {
+        // rows beyond those written have no page: bound the range by the rows the chain holds
+        int32_t written = 0;
+        int rc = dicegp_chain_status(c, 1, &chain, nullptr, &written, nullptr, nullptr, nullptr);
+        if (rc != DICEGP_OK) return rc;
+        if (first_row + n_rows > written) return c->fail(DICEGP_ERR_ARG, "download_trace: row range beyond the rows written so far");
+    }
     const int CT = c->hC[d.gene] * d.Tc;
     const size_t rowlen = 2 * (size_t)CT + 2;
     DG_CUDA(c, c->dgather.resize((size_t)n_rows * rowlen));

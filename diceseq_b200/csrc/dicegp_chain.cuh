@@ -302,6 +302,44 @@ __device__ __noinline__ void lik_warp_pass_log(const double *Wc, const int *rel,
 //   then K, S_A, Q_A, S_B, Q_B (CTm doubles each).
 // Returns 1 to every thread of the block when all columns pass.
 // ---------------------------------------------------------------------------------------
+// numpy's pairwise sum (np.add.reduce of a 1-D series) of n copies of v: blocks of <= 128 values with 8
+// accumulators (all equal here, so one is carried: their tree sum 8 r is exact), split in halves above that.
+__device__ __noinline__ double dg_np_const_sum(double v, int n) {
+    auto block = [&](int k) {
+        if (k < 8) {
+            double r = 0.0;
+            for (int i = 0; i < k; ++i) r += v;
+            return r;
+        }
+        double r = v;
+        int i = 8;
+        for (; i < k - (k % 8); i += 8) r += v;
+        double res = 8.0 * r;
+        for (; i < k; ++i) res += v;
+        return res;
+    };
+    if (n <= 128) return block(n);
+    int f_n[32], f_state[32], fs = 0, rs = 0;
+    double res[34];
+    f_n[0] = n; f_state[0] = 0; fs = 1;
+    while (fs > 0) {
+        const int k = fs - 1;
+        if (f_n[k] <= 128) { res[rs++] = block(f_n[k]); --fs; continue; }
+        int n2 = f_n[k] / 2;
+        n2 -= n2 % 8;
+        if (f_state[k] == 0) { f_state[k] = 1; f_n[fs] = n2; f_state[fs] = 0; ++fs; }
+        else if (f_state[k] == 1) { f_state[k] = 2; f_n[fs] = f_n[k] - n2; f_state[fs] = 0; ++fs; }
+        else { const double r = res[rs - 1], l = res[rs - 2]; rs -= 2; res[rs++] = l + r; --fs; }
+    }
+    return res[0];
+}
+// np.mean and np.var (two-pass, population) of n copies of v
+__device__ __noinline__ void dg_np_const_stats(double v, int n, double &mean, double &var) {
+    mean = dg_np_const_sum(v, n) / (double)n;
+    const double e = v - mean;
+    var = dg_np_const_sum(__dmul_rn(e, e), n) / (double)n;
+}
+
 __host__ __device__ inline int dg_geweke_state_len(int CTm) { return 4 + 5 * CTm; }
 
 // Runs on the `nwarps` warps (index `warp`) that synchronise on named barrier `bar_id`.
@@ -369,10 +407,22 @@ __device__ __noinline__ int geweke_converged(double *gw, double *gst, int CTm, i
             double va = qa / (double)nA - meanA * meanA, vb = qb / (double)nB - meanB * meanB;
             if (va < 0.0) va = 0.0;                       // rounding of an (almost) constant window
             if (vb < 0.0) vb = 0.0;
-            const double den = sqrt(va + vb);
+            double den = sqrt(va + vb), dmean = meanA - meanB;
+            if (sa == 0.0 && qa == 0.0 && sb == 0.0 && qb == 0.0) {
+                // a series that is constant over both windows (a chain that never moved: -inf likelihood,
+                // SURVEY Appendix B #9).  numpy's two-pass variance of n equal values is the square of the
+                // rounding error of its pairwise mean -- usually tiny but not zero, and then Z <= sqrt(2)
+                // and the reference calls the chain converged; only when both means are exact is Z None.
+                // Reproduce numpy's arithmetic for this case (O(n) adds; it ends the chain at the first check).
+                double mA, vA, mB, vB;
+                dg_np_const_stats(K, nA, mA, vA);
+                dg_np_const_stats(K, nB, mB, vB);
+                den = sqrt(vA + vB);
+                dmean = mA - mB;
+            }
             // reference: Z None (den == 0) or Z > 2 -> not converged; NaN compares false
             if (den == 0.0) ok = 0;
-            else if (fabs(meanA - meanB) / den > 2.0) ok = 0;
+            else if (fabs(dmean) / den > 2.0) ok = 0;
         }
         dg_bar(bar_id, nbar);
     }

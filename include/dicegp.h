@@ -182,6 +182,17 @@ int dicegp_run_host_stream(dicegp_ctx *ctx, int32_t n, const int32_t *chain_ids,
  */
 int dicegp_run_device_stream(dicegp_ctx *ctx, uint64_t seed, const int64_t *stream_id);
 
+/*
+ * The device-generated stream of one installed chain, written out instead of consumed: for steps
+ * [step0, step0 + n_steps) the proposal increments delta[s][c][t] = Y_try - Y_now (c < C-1, the
+ * role of np.random.multivariate_normal's output minus its mean, model_GP.py:329) and the
+ * uniforms u[s] (np.random.rand, model_GP.py:351), bit for bit what dicegp_run_device_stream
+ * feeds the chain with for (seed, stream_id).  A test instrument: replaying the dump through a
+ * CPU restatement of Psi_GP_MH step-checks the device-stream mode.  Synchronous.
+ */
+int dicegp_dump_stream(dicegp_ctx *ctx, int32_t chain, uint64_t seed, int64_t stream_id,
+                       int32_t step0, int32_t n_steps, double *delta, double *u);
+
 /* ------------------------------------------------------------------ results -------- */
 /*
  * Per-chain status: m_ret is the `m` the reference returns (model_GP.py:395: number of

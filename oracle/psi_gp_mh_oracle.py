@@ -187,14 +187,17 @@ class StepRecord:
 def psi_gp_mh(R_mat, len_isos, prob_isos, X=None, Ymean=None, var=None, theta1=3.0,
               theta2=None, M=20000, initial=1000, gap=500, randomS=None, theta2_std=1.0,
               theta2_low=0.00001, theta2_up=100, *, rng=None, record=None,
-              faithful_cost=False):
+              faithful_cost=False, replay=None):
     """MH sampler with GP prior, restating model_GP.py:188-395.
 
     Same arguments / return tuple as the reference:
     (Psi_all (m,C,T), Y_all (m,C,T), theta2_all (m,C-1), Pro_all (m,), Lik_all (m,), cnt, m).
     Extra keyword-only arguments: `rng` (a RandomState; default the global legacy state),
     `record` (a StepRecord), `faithful_cost` (redo inv/det/svd every step like the
-    reference; same bits, reference-like cost).
+    reference; same bits, reference-like cost), `replay` = (delta (M, C-1, T), u (M,)): take the
+    proposal increments (the value of `np.dot(z, A)` in numpy's multivariate_normal, :329) and the
+    uniforms (:351) from these arrays instead of drawing them -- used to step-check a stream that
+    was generated elsewhere (the device's Philox stream); fixed-theta2 mode only.
     """
     T = len(len_isos)
     C = len(len_isos[0])
@@ -281,8 +284,11 @@ def psi_gp_mh(R_mat, len_isos, prob_isos, X=None, Ymean=None, var=None, theta1=3
                 pc = _MvnConst(cov_try[:, :, c])
             else:
                 A, jc, pc = fac_c[c], jump_c[c], prior_c[c]
-            z = stream.normals(T)
-            step = np.dot(z.reshape(1, -1), A)                 # numpy multivariate_normal body
+            if replay is not None:
+                step = np.array(replay[0][m, c], dtype=float).reshape(1, -1)
+            else:
+                z = stream.normals(T)
+                step = np.dot(z.reshape(1, -1), A)             # numpy multivariate_normal body
             if record is not None:
                 record.delta.append(step[0].copy())
             step += Y_now[c, :]
@@ -305,7 +311,7 @@ def psi_gp_mh(R_mat, len_isos, prob_isos, X=None, Ymean=None, var=None, theta1=3
             L_try += lt
 
         alpha = np.exp(min(P_try + Q_now - P_now - Q_try, 0))  # :348
-        u = stream.uniform()                                   # :351 (np.random.rand(1))
+        u = replay[1][m] if replay is not None else stream.uniform()   # :351 (np.random.rand(1))
         accepted = bool(u < alpha)
         if record is not None:
             record.u.append(u)

@@ -78,3 +78,22 @@ def test_recorder_replays():
         if acc[s]:
             y = delta[s] + y
         np.testing.assert_array_equal(Y[s, 0, :], y)
+
+
+def test_replay_mode_reproduces_a_recorded_run():
+    """`replay=(delta, u)` feeds psi_gp_mh a stream generated elsewhere (tests/test_gpu_device_stream.py
+    replays the device's Philox stream); replaying the oracle's own recorded stream must give back the
+    very same run, without touching any random state."""
+    R, L, P, kw, z = load_golden("ts_t8_c4")
+    rec = orc.StepRecord()
+    a = orc.psi_gp_mh([r.copy() for r in R], [l.copy() for l in L], [p.copy() for p in P], record=rec, **kw)
+    delta, u, _acc, _pt, _lt = rec.arrays()
+    C, T = a[0].shape[1], a[0].shape[2]
+    delta = delta.reshape(-1, C - 1, T)
+    state = np.random.get_state()
+    kw2 = dict(kw, randomS=None)
+    b = orc.psi_gp_mh(R, L, P, replay=(delta, u), **kw2)
+    assert np.array_equal(np.random.get_state()[1], state[1])
+    assert a[5] == b[5] and a[6] == b[6]
+    for x, y in zip(a[:5], b[:5]):
+        assert np.array_equal(x, y)
