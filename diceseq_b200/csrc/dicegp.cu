@@ -19,6 +19,7 @@ constexpr int DICEGP_CHAIN_EXHAUSTED_ = 2;
 constexpr int DICEGP_CHAIN_NOMEM_ = 3;
 }  // namespace dg
 #include "dicegp_chain.cuh"
+#include "dicegp_wide.cuh"
 #include "dicegp_prerun.cuh"
 
 // =======================================================================================
@@ -481,7 +482,7 @@ struct dicegp_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     cudaStream_t class_stream[16] = {};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[64] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[96] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     int64_t total_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     int use_tma = 1;
 
@@ -529,6 +530,8 @@ struct dicegp_ctx {
     DevBuf<int64_t> soff;
     DevBuf<int32_t> sids;
     DevBuf<unsigned long long> dprof;
+    DevBuf<unsigned long long> dctr;        // work counters of the chain kernels (ChainTab::ctr)
+    size_t static_smem_wide = 0;
     double last_ms = 0.0;
     int64_t last_launches = 0, last_evals = 0, last_steps = 0;
     std::vector<int32_t> hm_next_before;
@@ -568,13 +571,15 @@ ChainTab make_chain_tab(dicegp_ctx *c) {
     t.stream_id = c->have_stream_id ? c->cstream_id.p : nullptr;
     t.trace = c->ctrace.p; t.st = c->cst.p; t.m_next = c->cm_next.p; t.cnt = c->ccnt.p;
     t.state = c->cstate.p; t.m_ret = c->cm_ret.p; t.flags = c->cflags.p;
+    t.ctr = c->dctr.p;
     return t;
 }
 
 // Residency tiers: W resident in shared memory at 8/4/2/1 blocks per SM, then the tier
 // that streams W from L2/HBM every step.  Each tier is further split by isoform count,
 // because the likelihood loop is compiled per C (weights f[C] in registers).
-constexpr int kTiers = 8;                     // 0-3 resident, 4 streamed, 5-7 streamed over a cluster of 2/4/8 blocks
+constexpr int kTiers = 9;                     // 0-3 resident, 4 streamed, 5-7 streamed over a cluster of 2/4/8 blocks, 8 wide rounds (dicegp_wide.cuh)
+constexpr int kWideTier = 8;
 constexpr int kKinds = 8;                      // kernel variants by C: generic, 2..8
 constexpr int kGroups = kTiers * kKinds;
 void launch_classes(const dicegp_ctx *c, LaunchClass out[kTiers]) {
@@ -588,11 +593,12 @@ void launch_classes(const dicegp_ctx *c, LaunchClass out[kTiers]) {
     }
     out[4] = {256, 0, 2, false};
     for (int i = 5; i < kTiers; ++i) out[i] = {DG_LB_THREADS, 0, 1, false};
+    out[kWideTier] = {DG_WIDE_THREADS, 0, 1, false};
     // development overrides: DICEGP_TIER_THREADS / DICEGP_TIER_BPS = five comma-separated ints
     const char *et = getenv("DICEGP_TIER_THREADS"), *eb = getenv("DICEGP_TIER_BPS");
     if (et) sscanf(et, "%d,%d,%d,%d,%d", &out[0].threads, &out[1].threads, &out[2].threads, &out[3].threads, &out[4].threads);
     if (eb) sscanf(eb, "%d,%d,%d,%d,%d", &out[0].blocks_per_sm, &out[1].blocks_per_sm, &out[2].blocks_per_sm, &out[3].blocks_per_sm, &out[4].blocks_per_sm);
-    for (int i = 0; i < kTiers; ++i) {
+    for (int i = 0; i < kWideTier; ++i) {
         if (out[i].threads > DG_LB_THREADS) out[i].threads = DG_LB_THREADS;
         // register file: DG_LB_THREADS threads per SM at the compiled register count
         if (out[i].threads * out[i].blocks_per_sm > DG_LB_THREADS) out[i].blocks_per_sm = DG_LB_THREADS / out[i].threads;
@@ -604,7 +610,7 @@ size_t fixed_smem_bytes(int C, int Tc, int threads, bool streamed, int cs = 1) {
     const int nodes = streamed ? dg_nodes_streamed(C <= 8 ? C : 0) : DG_NODES_RESIDENT;
     return (size_t)dg_layout(C, Tc, (threads + 31) / 32, nodes, cs).total * sizeof(double);
 }
-inline int tier_cluster(int tier) { return tier < 5 ? 1 : (2 << (tier - 5)); }
+inline int tier_cluster(int tier) { return (tier < 5 || tier == kWideTier) ? 1 : (2 << (tier - 5)); }
 
 int64_t chain_reads(const dicegp_ctx *c, int chain) {
     const dicegp_chain_desc &d = c->hdesc[chain];
@@ -644,6 +650,70 @@ int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain, int
         if (fixed_smem_bytes(C, d.Tc, cls[i].threads, false) + (size_t)wb <= cls[i].smem_limit) return i;
     }
     return 4;
+}
+
+// ---- wide-round kernel (dicegp_wide.cuh): launch shape per isoform count ----------------------
+struct WidePlan { int ncw, bps, rj; };
+inline int env_int(const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; }
+WidePlan wide_plan(int C, int latency_mode) {
+    // 16 consumer warps on a whole SM for wide genes (their W then stays L2 resident: 148 x <= 512 KB)
+    // and in the straggler pass; two blocks of 8 consumer warps per SM for narrow genes (the serial part of
+    // one chain's round overlaps the likelihood pass of the other).  DICEGP_WIDE_NCW / _BPS / _RJ override.
+    static const int e_ncw = env_int("DICEGP_WIDE_NCW", 0), e_bps = env_int("DICEGP_WIDE_BPS", 0), e_rj = env_int("DICEGP_WIDE_RJ", 0);
+    WidePlan p;
+    p.rj = (e_rj == 2 || e_rj == 4) ? e_rj : 4;
+    (void)latency_mode; (void)C;
+    p.ncw = 16; p.bps = 1;
+    if (e_ncw > 0) p.ncw = std::min(e_ncw, DG_WIDE_THREADS / 32 - 1);
+    if (e_bps > 0) p.bps = e_bps;
+    if (32 * (p.ncw + 1) * p.bps > DG_WIDE_THREADS) p.bps = std::max(1, DG_WIDE_THREADS / (32 * (p.ncw + 1)));
+    return p;
+}
+inline size_t wide_fixed_bytes(int C, int Tc, const WidePlan &p) {
+    return (size_t)dg::dg_wide_layout(C, Tc, p.ncw, 4 * p.rj).ring * sizeof(double);
+}
+inline size_t wide_budget(const dicegp_ctx *c, const WidePlan &p) {
+    return std::min<size_t>(233472 / p.bps - 1024, c->smem_optin - c->static_smem_wide);
+}
+bool wide_eligible(const dicegp_ctx *c, int chain, int latency_mode) {
+    // DICEGP_WIDE: 0 never, 1 (default) the straggler pass only, 2 every pass.  In the throughput pass two to
+    // four chains of the general kernel per SM overlap each other's serial parts and spend a third less fp64
+    // work per committed step (4 candidates per round instead of 16); with one chain per SM, W L2 resident
+    // and acceptance rates of a few per cent (the chains still running after 4096 steps) the wide rounds win.
+    static const int mode = env_int("DICEGP_WIDE", 1);
+    if (mode == 0 || (mode == 1 && !latency_mode)) return false;
+    const dicegp_chain_desc &d = c->hdesc[chain];
+    const int C = c->hC[d.gene];
+    if (C < 2 || C * d.Tc > DG_WIDE_MAXCT) return false;
+    const WidePlan p = wide_plan(C, latency_mode);
+    const size_t stage = (size_t)p.ncw * C * 256;
+    return wide_fixed_bytes(C, d.Tc, p) + 2 * stage <= wide_budget(c, p);
+}
+
+typedef void (*wide_kernel_t)(GeneTab, ChainTab, StreamArgs, const int32_t *, int, int, int, int *);
+wide_kernel_t wide_kernel_for(int kind, int rj) {
+    if (rj == 2) {
+        switch (kind) {
+            case 0: return dicegp_wide_kernel<0, 2>;
+            case 1: return dicegp_wide_kernel<2, 2>;
+            case 2: return dicegp_wide_kernel<3, 2>;
+            case 3: return dicegp_wide_kernel<4, 2>;
+            case 4: return dicegp_wide_kernel<5, 2>;
+            case 5: return dicegp_wide_kernel<6, 2>;
+            case 6: return dicegp_wide_kernel<7, 2>;
+            default: return dicegp_wide_kernel<8, 2>;
+        }
+    }
+    switch (kind) {
+        case 0: return dicegp_wide_kernel<0, 4>;
+        case 1: return dicegp_wide_kernel<2, 4>;
+        case 2: return dicegp_wide_kernel<3, 4>;
+        case 3: return dicegp_wide_kernel<4, 4>;
+        case 4: return dicegp_wide_kernel<5, 4>;
+        case 5: return dicegp_wide_kernel<6, 4>;
+        case 6: return dicegp_wide_kernel<7, 4>;
+        default: return dicegp_wide_kernel<8, 4>;
+    }
 }
 
 // Chains that run on a cluster never allocate trace pages on the device (only the lead block
@@ -723,6 +793,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
         const dicegp_chain_desc &d = c->hdesc[ids[i]];
         const int C = c->hC[d.gene];
         int tier = pick_tier(c, cls, ids[i], latency_mode);
+        if (tier <= 4 && wide_eligible(c, ids[i], latency_mode)) tier = kWideTier;   // wide rejection-chain rounds
         if (latency_mode == 2 && tier == 4) tier = 6;          // last stragglers: a cluster of 4 blocks each
         const int k = tier * kKinds + kind_of(C);
         by_group[k].push_back(ids[i]);
@@ -779,7 +850,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     int64_t launches = 0;
     int next_stream = 0;
     // big tiers first: the 1-block-per-SM and streaming launches carry most of the work
-    const int tier_order[kTiers] = {7, 6, 5, 4, 3, 2, 1, 0};
+    const int tier_order[kTiers] = {7, 6, 5, kWideTier, 4, 3, 2, 1, 0};
     for (int to = 0; to < kTiers; ++to) {
         for (int kind_i = 0; kind_i < kKinds; ++kind_i) {
             // straggler pass: many isoforms first (most of the chains that use all M steps are those)
@@ -788,6 +859,46 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             const int k = tier * kKinds + kind;
             const int n_ids = (int)by_group[k].size();
             if (n_ids == 0) continue;
+            if (tier == kWideTier) {
+                int maxC = 2;
+                for (int32_t id : by_group[k]) maxC = std::max(maxC, c->hC[c->hdesc[id].gene]);
+                const WidePlan wp = wide_plan(kind == 0 ? maxC : kind + 1, latency_mode);
+                size_t fixed = 0;
+                for (int32_t id : by_group[k]) {
+                    const dicegp_chain_desc &d = c->hdesc[id];
+                    fixed = std::max(fixed, wide_fixed_bytes(c->hC[d.gene], d.Tc, wp));
+                }
+                const size_t budget = wide_budget(c, wp);
+                const size_t ring_bytes = (budget - fixed) & ~(size_t)127;
+                const size_t smem = fixed + ring_bytes;
+                cudaStream_t st = c->class_stream[next_stream];
+                next_stream = (next_stream + 1) % kStreams;
+                DG_CUDA(c, cudaStreamWaitEvent(st, c->ev_fork, 0));
+                StreamArgs sak = sa;
+                if (delta_off) {
+                    sak.delta_off = c->ddoff.p + base[k];
+                    sak.u_off = c->ddoff.p + flat.size() + base[k];
+                }
+                int grid = n_ids;
+                int *queue = nullptr;
+                if (persistent) {
+                    grid = std::min(n_ids, c->sm_count * wp.bps);
+                    queue = c->dqueue.p + k;
+                }
+                wide_kernel_t kern = wide_kernel_for(kind, wp.rj);
+                DG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(c->smem_optin - c->static_smem_wide)));
+                kern<<<grid, 32 * (wp.ncw + 1), smem, st>>>(gt, ct, sak, c->dids.p + base[k], n_ids, n_steps, (int)ring_bytes, queue);
+                {
+                    cudaError_t e = cudaGetLastError();
+                    if (e != cudaSuccess) return c->cuda_fail(e, "wide chain kernel launch");
+                }
+                ++launches;
+                ++c->total_launches;
+                DG_CUDA(c, cudaEventRecord(c->ev_join[k], st));
+                DG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[k], 0));
+                continue;
+            }
             // launch shape: resident tiers use the tier's block size; the streaming tier plans
             // (likelihood warps per chain, chains per SM) from the group's shapes so that as many
             // streaming warps as possible are resident: threads*k <= DG_LB_THREADS (registers),
@@ -912,12 +1023,23 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     {
         unsigned long long h[16];
         DG_CUDA(c, cudaMemcpy(h, c->dprof.p, sizeof h, cudaMemcpyDeviceToHost));
-        const char *nm[9] = {"S", "window", "B2wait", "decide", "update", "geweke", "-", "-", "-"};
-        double n = (double)std::max<unsigned long long>(h[10], 1);
-        fprintf(stderr, "[dg_prof] steps=%llu cycles/step:", h[10]);
-        double tot = 0;
-        for (int i = 0; i < 6; ++i) { fprintf(stderr, " %s=%.0f", nm[i], h[i] / n); tot += h[i] / n; }
-        fprintf(stderr, " total=%.0f\n", tot);
+        // general kernel: S, window, B2wait, decide, update, geweke; wide kernel: S, wait f, likelihood, wait
+        // partials, decide + new state, wait state, rows (+ geweke), aux warp busy; h[11] = rounds (wide)
+        if (h[11]) {
+            double n = (double)h[11];
+            fprintf(stderr, "[dg_prof] wide: steps=%llu rounds=%llu (%.2f steps/round) cycles/round:", h[10], h[11], h[10] / n);
+            const char *nm[8] = {"S", "waitf", "lik", "waitp", "decide", "waits", "rows", "aux"};
+            double tot = 0;
+            for (int i = 0; i < 8; ++i) { fprintf(stderr, " %s=%.0f", nm[i], h[i] / n); if (i < 7) tot += h[i] / n; }
+            fprintf(stderr, " total=%.0f\n", tot);
+        } else {
+            const char *nm[9] = {"S", "window", "B2wait", "decide", "update", "geweke", "-", "-", "-"};
+            double n = (double)std::max<unsigned long long>(h[10], 1);
+            fprintf(stderr, "[dg_prof] steps=%llu cycles/step:", h[10]);
+            double tot = 0;
+            for (int i = 0; i < 6; ++i) { fprintf(stderr, " %s=%.0f", nm[i], h[i] / n); tot += h[i] / n; }
+            fprintf(stderr, " total=%.0f\n", tot);
+        }
     }
 #endif
     return DICEGP_OK;
@@ -1049,17 +1171,25 @@ int dicegp_create(int device, dicegp_ctx **out) {
             return DICEGP_ERR_CUDA;
         }
         c->static_smem = std::max(fa0.sharedSizeBytes, fa1.sharedSizeBytes);
+        cudaFuncAttributes fw;
+        if (cudaFuncGetAttributes(&fw, dicegp_wide_kernel<0, 4>) != cudaSuccess) {
+            g_last_error = std::string("kernel image not loadable on this device: ") + cudaGetErrorString(cudaGetLastError());
+            delete c;
+            return DICEGP_ERR_CUDA;
+        }
+        c->static_smem_wide = fw.sharedSizeBytes;
     }
     const char *no_tma = getenv("DICEGP_NO_TMA");
     c->use_tma = (no_tma && no_tma[0] == '1') ? 0 : 1;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) goto fail;
     for (int k = 0; k < kStreams; ++k)
         if (cudaStreamCreateWithFlags(&c->class_stream[k], cudaStreamNonBlocking) != cudaSuccess) goto fail;
-    for (int k = 0; k < 64; ++k)
+    for (int k = 0; k < 96; ++k)
         if (cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) goto fail;
     if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) goto fail;
     if (cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess) goto fail;
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) goto fail;
+    if (c->dctr.resize(8) != cudaSuccess || cudaMemset(c->dctr.p, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) goto fail;
     *out = c;
     return DICEGP_OK;
 fail:
@@ -1081,14 +1211,14 @@ int dicegp_destroy(dicegp_ctx *c) {
     c->dgather.release(); c->cst_off.release(); c->cstream_id.release();
     c->cprior.release(); c->cpool.release(); c->ctrace.release(); c->cst.release();
     c->dids.release(); c->ddoff.release(); c->ddelta.release(); c->du.release(); c->dvar.release();
-    c->dqueue.release(); c->deval.release(); c->deval_done.release();
+    c->dqueue.release(); c->deval.release(); c->deval_done.release(); c->dctr.release(); c->dprof.release();
     c->smean.release(); c->sci.release(); c->slik.release(); c->soff.release(); c->sids.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
-    for (int k = 0; k < 64; ++k)
+    for (int k = 0; k < 96; ++k)
         if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
     for (int k = 0; k < kStreams; ++k)
         if (c->class_stream[k]) cudaStreamDestroy(c->class_stream[k]);

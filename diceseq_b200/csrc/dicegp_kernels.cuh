@@ -53,6 +53,9 @@ struct ChainTab {
     double *trace;
     double *st;                  // ynow[C*Tc], psinow[C*Tc], P_now, L_now
     int32_t *m_next, *cnt, *state, *m_ret, *flags;
+    // work counters (may be NULL): [0] bytes of W brought from L2 / HBM into shared memory or registers,
+    // [1] rounds (passes over W), [2] candidate evaluations (rounds x candidates x reads), [3] steps
+    unsigned long long *ctr;
 };
 
 struct StreamArgs {
