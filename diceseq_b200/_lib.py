@@ -25,7 +25,7 @@ SYMBOLS = (
     "dicegp_chain_status", "dicegp_download_trace", "dicegp_posterior_summary",
     "dicegp_last_run_stats", "dicegp_set_trace_budget", "dicegp_set_prerun_chains",
     "dicegp_timer_start", "dicegp_timer_stop", "dicegp_counters", "dicegp_eval_loglik",
-    "dicegp_dump_stream",
+    "dicegp_dump_stream", "dicegp_work_counters",
 )
 
 
@@ -88,6 +88,7 @@ def load():
     lib.dicegp_counters.argtypes = [vp, pi64, pi64, pi64]
     lib.dicegp_eval_loglik.argtypes = [vp, i32, i32, i32, pd, pd]
     lib.dicegp_dump_stream.argtypes = [vp, i32, C.c_uint64, i64, i32, i32, pd, pd]
+    lib.dicegp_work_counters.argtypes = [vp, pi64, i32, i32]
     for name in SYMBOLS:
         if name != "dicegp_last_error":
             getattr(lib, name).restype = C.c_int
@@ -205,6 +206,12 @@ class Context:
         a, b, d = C.c_int64(), C.c_int64(), C.c_int64()
         self._check(self.lib.dicegp_counters(self._h, C.byref(a), C.byref(b), C.byref(d)))
         return {"kernel_launches": a.value, "h2d_bytes": b.value, "d2h_bytes": d.value}
+
+    def work_counters(self, reset=False):
+        """What the chain kernels counted since the last reset (dicegp_work_counters)."""
+        v = np.zeros(8, dtype=np.int64)
+        self._check(self.lib.dicegp_work_counters(self._h, _p(v, C.c_int64), 8, 1 if reset else 0))
+        return dict(zip(("w_bytes", "rounds", "candidate_evals", "steps", "fma"), (int(x) for x in v[:5])))
 
     def main_chains_from_prerun(self, M, initial, gap, theta1, kinv, prop_factor, prior_const):
         kinv = _f64(kinv)

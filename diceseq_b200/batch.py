@@ -136,6 +136,7 @@ class BatchSampler:
 
     def _acc_stats(self, phase):
         s = self.ctx.last_run_stats()
+        s.update(self.ctx.work_counters(reset=True))     # what the kernels of this run counted themselves
         for k, v in s.items():
             self.stats[k] = self.stats.get(k, 0) + v
             self.stats[phase + "_" + k] = self.stats.get(phase + "_" + k, 0) + v

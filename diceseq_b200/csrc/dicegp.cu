@@ -1803,6 +1803,18 @@ int dicegp_counters(dicegp_ctx *c, int64_t *kernel_launches, int64_t *h2d_bytes,
     return DICEGP_OK;
 }
 
+int dicegp_work_counters(dicegp_ctx *c, int64_t *out, int32_t n_out, int32_t reset) {
+    if (!c) return DICEGP_ERR_ARG;
+    if (!out || n_out < 0) return c->fail(DICEGP_ERR_ARG, "work_counters: NULL buffer");
+    DG_CUDA(c, cudaSetDevice(c->device));
+    unsigned long long h[8];
+    DG_CUDA(c, cudaMemcpyAsync(h, c->dctr.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    if (reset) DG_CUDA(c, cudaMemsetAsync(c->dctr.p, 0, sizeof h, c->stream));
+    DG_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n_out && i < 8; ++i) out[i] = (int64_t)h[i];
+    return DICEGP_OK;
+}
+
 int dicegp_set_prerun_chains(dicegp_ctx *c, double theta1, double var0, int32_t M, int32_t initial, int32_t gap) {
     if (!c) return DICEGP_ERR_ARG;
     if (c->G == 0) return c->fail(DICEGP_ERR_STATE, "set_prerun_chains: upload genes first");

@@ -719,7 +719,9 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     int next_check = m > initial ? m : initial;
     next_check += (gap - next_check % gap) % gap;
     int rbase = m % RING;                                 // ring slot of step m
+    unsigned long long nrounds = 0;                       // passes over W (thread 0 reports them)
     while (m < m_end || init) {
+        ++nrounds;
         // steps this round may commit: up to D, not past the chunk, not past a check step
         const int nd_max = init ? 0 : min(shape ? DM : DT, min(m_end - m, next_check - m + 1));
         // ================= S phase (state warps): candidates -> f =================
@@ -1048,6 +1050,13 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             ct.flags[chain] = flags;
             ct.m_ret[chain] = m_ret;
             ct.state[chain] = state;
+            if (ct.ctr) {                                 // work counters: W bytes brought on chip, rounds, candidate evaluations, steps
+                atomicAdd(ct.ctr + 0, W_IN_SMEM ? (unsigned long long)wbytes : nrounds * (unsigned long long)wbytes);
+                atomicAdd(ct.ctr + 1, nrounds);
+                atomicAdd(ct.ctr + 2, nrounds * (unsigned long long)J * (unsigned long long)r_total);
+                atomicAdd(ct.ctr + 3, (unsigned long long)(m - m_start));
+                atomicAdd(ct.ctr + 4, nrounds * (unsigned long long)J * (unsigned long long)r_total * (unsigned long long)C);
+            }
         }
         if (W_IN_SMEM && use_tma)
             asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(dg_smem_u32(mbar)) : "memory");

@@ -54,7 +54,8 @@ struct ChainTab {
     double *st;                  // ynow[C*Tc], psinow[C*Tc], P_now, L_now
     int32_t *m_next, *cnt, *state, *m_ret, *flags;
     // work counters (may be NULL): [0] bytes of W brought from L2 / HBM into shared memory or registers,
-    // [1] rounds (passes over W), [2] candidate evaluations (rounds x candidates x reads), [3] steps
+    // [1] rounds (passes over W), [2] candidate evaluations (rounds x candidates x reads), [3] steps,
+    // [4] fp64 fused multiply-adds of those evaluations (x isoforms)
     unsigned long long *ctr;
 };
 

@@ -194,6 +194,7 @@ dicegp_prerun_kernel(GeneTab gt, ChainTab ct, uint64_t seed, const int32_t *__re
         double *st = ct.st + ct.st_off[chain];
         double *gst = st + rowlen;                                        // running Geweke sums
         int m = ct.m_next[chain];
+        const int m_first = m;
         const int m_end = (m + n_steps < M) ? m + n_steps : M;
         double y_now = 0.0, psi_now = 0.0, P_now = 0.0, L_now = 0.0;
         int cnt = 0, flags = 0, state = 0, m_ret = 0;
@@ -307,6 +308,14 @@ dicegp_prerun_kernel(GeneTab gt, ChainTab ct, uint64_t seed, const int32_t *__re
             ct.flags[chain] = flags;
             ct.m_ret[chain] = m_ret;
             ct.state[chain] = state;
+            if (ct.ctr) {
+                const unsigned long long ev = (unsigned long long)(m - m_first) + (m_first == 0 ? 1ull : 0ull);
+                atomicAdd(ct.ctr + 0, (unsigned long long)C * npairs * 16ull);
+                atomicAdd(ct.ctr + 1, ev);
+                atomicAdd(ct.ctr + 2, ev * 2ull * (unsigned long long)npairs);
+                atomicAdd(ct.ctr + 3, (unsigned long long)(m - m_first));
+                atomicAdd(ct.ctr + 4, ev * 2ull * (unsigned long long)npairs * (unsigned long long)C);
+            }
         }
     }
 }

@@ -743,6 +743,7 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
             atomicAdd(ct.ctr + 1, rounds);
             atomicAdd(ct.ctr + 2, rounds * (unsigned long long)J * (unsigned long long)(rel[Tc]));
             atomicAdd(ct.ctr + 3, (unsigned long long)(m - m_start));
+            atomicAdd(ct.ctr + 4, rounds * (unsigned long long)J * (unsigned long long)(rel[Tc]) * (unsigned long long)C);
         }
         for (int s = 0; s < D; ++s)
             asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(dg_smem_u32(fullb + s)) : "memory");

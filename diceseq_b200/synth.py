@@ -44,9 +44,8 @@ def _n_reads(cid, rng, T, reads):
     return np.full(T, reads, dtype=np.int64)
 
 
-def gene_matrices(config, g, reads=1000, T=None, C=None):
-    """(R_list, len_list, prob_list) of gene number g of a named config, in the exact form
-    `Psi_GP_MH` takes them (lists over time points)."""
+def _gene_header(config, g, reads, T, C):
+    """The draws that fix a gene's shape: (rng, cid, T, C, L, psi (C, T), reads per time point)."""
     spec = CONFIGS[config]
     cid = spec["cid"]
     T = spec["T"] if T is None else T
@@ -64,6 +63,20 @@ def gene_matrices(config, g, reads=1000, T=None, C=None):
         e = np.exp(y - y.max(axis=0))
         psi = e / e.sum(axis=0)
     n_t = _n_reads(cid, rng, T, reads)
+    return rng, cid, T, C, L, psi, n_t
+
+
+def gene_shape(config, g, reads=1000, T=None, C=None):
+    """(isoforms, reads per time point) of gene g without generating its matrices: what the
+    read-count-balanced partition over GPUs needs (diceseq_b200/partition.py)."""
+    _rng, _cid, _T, C, _L, _psi, n_t = _gene_header(config, g, reads, T, C)
+    return C, n_t
+
+
+def gene_matrices(config, g, reads=1000, T=None, C=None):
+    """(R_list, len_list, prob_list) of gene number g of a named config, in the exact form
+    `Psi_GP_MH` takes them (lists over time points)."""
+    rng, cid, T, C, L, psi, n_t = _gene_header(config, g, reads, T, C)
     R_list, len_list, prob_list = [], [], []
     for t in range(T):
         n = int(n_t[t])

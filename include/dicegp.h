@@ -251,6 +251,15 @@ int dicegp_timer_stop(dicegp_ctx *ctx, double *elapsed_ms);
 int dicegp_counters(dicegp_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes,
                     int64_t *d2h_bytes);
 
+/* Work the chain kernels themselves counted since the last reset (a few atomic adds per chain and
+ * launch), out[0 .. n_out), n_out <= 8:
+ *   [0] bytes of W brought from L2 / HBM into shared memory (a resident chain counts its W once per launch,
+ *       a streamed chain once per round), [1] rounds = passes over W, [2] candidate evaluations = read
+ *       likelihoods evaluated including speculated candidates that were not committed (rounds x candidates
+ *       x reads), [3] MH steps committed, [4] fp64 fused multiply-adds of [2] (x isoforms).
+ * For the roofline figures of bench.py. */
+int dicegp_work_counters(dicegp_ctx *ctx, int64_t *out, int32_t n_out, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

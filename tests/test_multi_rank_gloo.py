@@ -81,3 +81,54 @@ def test_world2_gloo_gather_equals_single_process():
         assert p.exitcode == 0
     assert got == single
     assert [g[0] for g in got] == list(ids)
+
+
+class FakeBatch:
+    """BatchResult-shaped output keyed by the global gene id (what gather_batch ships)."""
+
+    def __init__(self, packed, gene_ids):
+        G, T = packed.G, packed.T
+        self.T, self.n_iso = T, packed.n_iso
+        ids = np.asarray(gene_ids)
+        self.m = (ids * 7 % 1000).astype(np.int32)
+        self.cnt = (ids * 3 % 100).astype(np.int32)
+        self.state = (ids % 3).astype(np.int32)
+        self.flags = np.zeros(G, dtype=np.int32)
+        self.lik_marg = -ids.astype(float) / 3
+        self.psi_mean = np.concatenate([np.full(int(c) * T, float(i)) + np.arange(int(c) * T) for i, c in zip(ids, packed.n_iso)])
+        self.psi_ci = np.repeat(self.psi_mean, 2) + 0.5
+
+
+class FakeBatchSampler:
+    def run(self, packed, gene_ids=None, **kw):
+        return FakeBatch(packed, gene_ids)
+
+
+def _worker_batch(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = partition.sample_sharded(_genes(23), np.arange(100, 123), FakeBatchSampler, rank, world, _batch_results=True)
+    if rank == 0:
+        q.put({k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in res.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_batch_world2_equals_single_process():
+    """The tensor gather of the summaries (gather_batch: one all_gather of lengths + one padded gather)
+    returns, on rank 0, exactly what a single process computes, in global gene order."""
+    single = partition.sample_sharded(_genes(23), np.arange(100, 123), FakeBatchSampler, 0, 1, _batch_results=True)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + 7
+    procs = [ctx.Process(target=_worker_batch, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert set(got) == set(single)
+    for k, v in single.items():
+        assert np.array_equal(np.asarray(got[k]), np.asarray(v)), k
+    assert list(got["gene_ids"]) == list(range(100, 123))
