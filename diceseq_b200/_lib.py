@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DICEGP_LIB") or os.path.join(_HERE, "libdicegp.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 CHAIN_RUNNING, CHAIN_CONVERGED, CHAIN_EXHAUSTED, CHAIN_NOMEM = 0, 1, 2, 3
 
@@ -48,7 +48,8 @@ class ChainDesc(C.Structure):
 
 class Limits(C.Structure):
     _fields_ = [("max_isoforms", C.c_int32), ("max_times", C.c_int32),
-                ("abi_version", C.c_int32), ("sm_count", C.c_int32)]
+                ("abi_version", C.c_int32), ("sm_count", C.c_int32),
+                ("max_latent", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -128,6 +129,15 @@ class ChainShapes:
 
     def __getitem__(self, i):
         return int(self.C[i]), int(self.Tc[i]), int(self.M[i])
+
+
+def shape_limits():
+    """Compiled shape limits of the library (no device needed): dict of max_isoforms, max_times, max_latent."""
+    lim = Limits()
+    rc = load().dicegp_get_limits(None, C.byref(lim))
+    if rc != 0:
+        raise DiceGPError(rc, "dicegp_get_limits")
+    return {"max_isoforms": lim.max_isoforms, "max_times": lim.max_times, "max_latent": lim.max_latent}
 
 
 class Context:

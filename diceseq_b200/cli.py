@@ -11,7 +11,8 @@ worker; `.sample.gz` is written in text mode (Appendix
 `--bias` modes other than `unif` are refused (they need a reference FASTA and a bias file);
 `--thetas x learn` runs host-driven chains, one gene at a time, with the likelihood on the GPU
 (theta2_mode.py) and -- like the reference's sampler -- only handles two-isoform genes;
-extra flags `--device`, `--seed`, `--batch`.
+genes beyond the library's shape limits (isoforms, isoforms x time points) are named and skipped;
+extra flags `--device`, `--gpus` (shard the genes over the GPUs of the box), `--seed`, `--batch`.
 
     python -m diceseq_b200.cli -a anno.gtf -s t1.bam---t2.bam---t3.bam -t 1.5,2.5,5 -o out/joint --add_premRNA
 """
@@ -56,7 +57,9 @@ def build_parser():
     group.add_option("--mcmc", type="int", nargs=4, dest="mcmc_run", default=[0, 20000, 1000, 100],
                      help="Four arguments for in MCMC iterations: save_sample,max_run,min_run,gap_run. "
                           "[default: 0 20000 1000 100]")
-    group.add_option("--device", type="int", dest="device", default=0, help="GPU index [default: %default]")
+    group.add_option("--device", type="int", dest="device", default=0, help="GPU index (first GPU with --gpus) [default: %default]")
+    group.add_option("--gpus", type="int", dest="gpus", default=1,
+                     help="GPUs of this box to shard the genes over (read-count-balanced greedy partition) [default: %default]")
     group.add_option("--seed", type="int", dest="seed", default=0, help="seed of the device random stream")
     group.add_option("--batch", type="int", dest="batch", default=20000, help="genes per GPU batch")
     parser.add_option_group(group)
@@ -66,6 +69,59 @@ def build_parser():
 def _inputs_worker(args):
     gene, sam_list, FLmean, FLstd = args
     return gene_inputs(gene, sam_list, FLmean, FLstd)
+
+
+def sample_genes(idx, gene_inputs_list, device, batch, sample_num, run_kw, progress=None):
+    """Stage 2 on ONE GPU: the multi-isoform genes `idx` (annotation indices, used as the global gene ids of
+    the random streams) in batches of `batch` through BatchSampler (pre-runs, jump variance, joint chains,
+    summaries on the device).  Returns ({idx: GeneResult}, {idx: Y samples (n, C, T)}).  Runs in the CLI
+    process, or in one worker process per GPU with --gpus."""
+    from .batch import BatchSampler, PipelinedSampler
+    from .packer import clean_inputs, pack_genes
+    T = len(run_kw["X"])
+    where = {i: k for k, i in enumerate(idx)}
+    chunks = [idx[b0:b0 + batch] for b0 in range(0, len(idx), batch)]
+
+    def batches():
+        for ch in chunks:
+            packed_in = []
+            for i in ch:
+                R_all, len_all, prob_all, _count = gene_inputs_list[where[i]]
+                clean_inputs(R_all, len_all, prob_all)               # model_GP.py:250-264
+                packed_in.append(([R * P for R, P in zip(R_all, prob_all)], len_all))
+            yield pack_genes(packed_in, pinned=len(chunks) > 1), dict(run_kw, gene_ids=np.array(ch))
+
+    # several batches: the copy of batch k+1 overlaps the sampling of batch k (two contexts)
+    pipe = PipelinedSampler(device) if len(chunks) > 1 else None
+    single = BatchSampler(device) if len(chunks) == 1 else None
+
+    def run_all():
+        if pipe is not None:
+            for res, _st in pipe.run_stream(batches()):
+                yield res, pipe.current
+        elif single is not None:
+            for packed, kw in batches():
+                yield single.run(packed, **kw), single
+
+    results, samples, done = {}, {}, 0
+    for (res, sampler), ch in zip(run_all(), chunks):
+        for k, i in enumerate(ch):
+            results[i] = res[k]
+            if sample_num > 0:
+                m = res[k].m
+                n_keep = min(int(0.5 * m), sample_num)
+                if n_keep > 0:
+                    _psi, Y, _pro, _lik = sampler.ctx.download_trace(k, n_keep, first_row=int(m / 2))
+                    samples[i] = Y
+                else:
+                    samples[i] = np.zeros((0, int(res.n_iso[k]), T))
+        done += len(ch)
+        if progress:
+            progress(done)
+    for s_ in (pipe, single):
+        if s_ is not None:
+            s_.close()
+    return results, samples
 
 
 def main(argv=None):
@@ -130,8 +186,6 @@ def main(argv=None):
             inputs = pool.map(_inputs_worker, jobs, chunksize=max(1, len(jobs) // (8 * options.nproc)))
 
     # ---- stage 2: GPU sampling of the multi-isoform genes -----------------------------------
-    from .batch import BatchSampler, PipelinedSampler
-    from .packer import clean_inputs, pack_genes
     multi = [i for i, g in enumerate(genes) if g.tranNum > 1]
     results = {}
     samples = {}
@@ -160,49 +214,47 @@ def main(argv=None):
             print("\n[DICEseq] Warning: --thetas x learn only works for two-isoform genes (as in the reference); "
                   "no output for %d genes: %s" % (len(dropped), ",".join(dropped[:20]) + ("..." if len(dropped) > 20 else "")))
         multi = []
-    chunks = [multi[b0:b0 + options.batch] for b0 in range(0, len(multi), options.batch)]
+    # genes beyond the compiled shape limits of the library are named and skipped (the reference has no
+    # such limit; the rest of the run must not be lost to them)
+    from . import _lib
+    lim = _lib.shape_limits()
+    too_big = [i for i in multi if genes[i].tranNum > lim["max_isoforms"] or T > lim["max_times"]
+               or genes[i].tranNum * T > lim["max_latent"]]
+    if too_big:
+        print("[DICEseq] Warning: %d genes exceed the sampler's shape limits (isoforms <= %d, isoforms x time points <= %d); "
+              "no output for: %s" % (len(too_big), lim["max_isoforms"], lim["max_latent"],
+                                     ",".join(genes[i].geneID for i in too_big[:20]) + ("..." if len(too_big) > 20 else "")))
+        drop = set(too_big)
+        multi = [i for i in multi if i not in drop]
 
-    def batches():
-        for idx in chunks:
-            packed_in = []
-            for i in idx:
-                R_all, len_all, prob_all, _count = inputs[i]
-                clean_inputs(R_all, len_all, prob_all)               # model_GP.py:250-264
-                packed_in.append(([R * P for R, P in zip(R_all, prob_all)], len_all))
-            yield pack_genes(packed_in, pinned=len(chunks) > 1), dict(
-                X=X, theta1=theta1, theta2=theta2, M=Mmax, initial=Mmin, gap=Mgap, seed=options.seed,
-                gene_ids=np.array(idx))
-
-    # several batches: the copy of batch k+1 overlaps the sampling of batch k (two contexts)
-    pipe = (PipelinedSampler(options.device) if len(chunks) > 1 else None)
-    single = BatchSampler(options.device) if len(chunks) == 1 else None
-
-    def run_all():
-        if pipe is not None:
-            for res, _st in pipe.run_stream(batches()):
-                yield res, pipe.current
-        elif single is not None:
-            for packed, kw in batches():
-                yield single.run(packed, **kw), single
-
-    done = 0
-    for (res, sampler), idx in zip(run_all(), chunks):
-        for k, i in enumerate(idx):
-            results[i] = res[k]
-            if sample_num > 0:
-                m = res[k].m
-                n_keep = min(int(0.5 * m), sample_num)
-                if n_keep > 0:
-                    _psi, Y, _pro, _lik = sampler.ctx.download_trace(k, n_keep, first_row=int(m / 2))
-                    samples[i] = Y
-                else:
-                    samples[i] = np.zeros((0, genes[i].tranNum, T))
-        done += len(idx)
-        sys.stdout.write("\r[DICEseq] %d / %d genes sampled in %.1f sec." % (done, len(multi), time.time() - start_time))
-        sys.stdout.flush()
-    for s_ in (pipe, single):
-        if s_ is not None:
-            s_.close()
+    run_kw = dict(X=X, theta1=theta1, theta2=theta2, M=Mmax, initial=Mmin, gap=Mgap, seed=options.seed)
+    n_gpus = max(1, int(options.gpus))
+    if n_gpus == 1 or len(multi) < 2 * n_gpus:
+        def progress(done):
+            sys.stdout.write("\r[DICEseq] %d / %d genes sampled in %.1f sec." % (done, len(multi), time.time() - start_time))
+            sys.stdout.flush()
+        res_d, samp_d = sample_genes(multi, [inputs[i] for i in multi], options.device, options.batch, sample_num, run_kw, progress)
+        results.update(res_d)
+        samples.update(samp_d)
+    elif multi:
+        # one process per GPU (the reference fans genes over a process pool, diceseq.py:226-235): LPT partition on
+        # isoforms x reads, no communication but the final gather of the per-gene results
+        import multiprocessing
+        from .partition import gene_cost, lpt_partition
+        cost = gene_cost([genes[i].tranNum for i in multi], [sum(r.shape[0] for r in inputs[i][0]) for i in multi])
+        bins = lpt_partition(cost, n_gpus)
+        ctx = multiprocessing.get_context("spawn")
+        with ctx.Pool(n_gpus) as pool:
+            jobs2 = [pool.apply_async(sample_genes, ([multi[k] for k in b], [inputs[multi[k]] for k in b],
+                                                     options.device + r, options.batch, sample_num, run_kw))
+                     for r, b in enumerate(bins)]
+            for r, j in enumerate(jobs2):
+                res_d, samp_d = j.get()
+                results.update(res_d)
+                samples.update(samp_d)
+                sys.stdout.write("\r[DICEseq] GPU %d done: %d / %d genes sampled in %.1f sec." % (
+                    options.device + r, len(results), len(multi), time.time() - start_time))
+                sys.stdout.flush()
 
     # ---- stage 3: output, in annotation order -----------------------------------------------
     out_dir = os.path.dirname(options.out_file)
@@ -222,7 +274,7 @@ def main(argv=None):
             count = inputs[i][3]
             if g.tranNum > 1:
                 if i not in results:
-                    continue                                         # dropped in theta2-sampling mode
+                    continue                                         # dropped (theta2-sampling mode, shape limits)
                 r = results[i]
                 psi_mean, psi_95, lik_marg = r.psi_mean, r.psi_95, r.lik_marg
             else:

@@ -370,8 +370,11 @@ __device__ void dg_radix_select2(const unsigned long long *keys, int n, int rank
 
 __global__ void __launch_bounds__(DG_SUM_THREADS)
 dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, double *__restrict__ mean_out,
-                      double *__restrict__ ci_out, const int64_t *__restrict__ out_off, double *__restrict__ lik_out) {
-    extern __shared__ __align__(16) unsigned long long dg_keys[];
+                      double *__restrict__ ci_out, const int64_t *__restrict__ out_off, double *__restrict__ lik_out,
+                      unsigned long long *gkeys, size_t gstride) {
+    extern __shared__ __align__(16) unsigned long long dg_keys_smem[];
+    // one column of keys: in shared memory, or (chains that keep more rows than fit) in a global scratch row
+    unsigned long long *dg_keys = gkeys ? gkeys + (size_t)blockIdx.x * gstride : dg_keys_smem;
     __shared__ unsigned hist[512];
     __shared__ int sh[4];
     __shared__ double red[DG_SUM_THREADS / 32];
@@ -525,6 +528,7 @@ struct dicegp_ctx {
     DevBuf<double> ddelta, du, dvar;
     DevBuf<int> dqueue;
     DevBuf<double> smean, sci, slik;       // posterior summary scratch
+    DevBuf<unsigned long long> skeys;      // radix-select keys of chains too long for shared memory
     DevBuf<double> deval;                  // eval_loglik scratch: y | per-block partial sums | lik
     DevBuf<unsigned> deval_done;
     DevBuf<int64_t> soff;
@@ -1212,7 +1216,7 @@ int dicegp_destroy(dicegp_ctx *c) {
     c->cprior.release(); c->cpool.release(); c->ctrace.release(); c->cst.release();
     c->dids.release(); c->ddoff.release(); c->ddelta.release(); c->du.release(); c->dvar.release();
     c->dqueue.release(); c->deval.release(); c->deval_done.release(); c->dctr.release(); c->dprof.release();
-    c->smean.release(); c->sci.release(); c->slik.release(); c->soff.release(); c->sids.release();
+    c->smean.release(); c->sci.release(); c->slik.release(); c->skeys.release(); c->soff.release(); c->sids.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1233,6 +1237,8 @@ int dicegp_get_limits(const dicegp_ctx *ctx, dicegp_limits *out) {
     out->max_times = DG_MAXT;
     out->abi_version = DICEGP_ABI_VERSION;
     out->sm_count = ctx ? ctx->sm_count : 0;
+    out->max_latent = DG_LB_THREADS - 64;     // state warps (one lane per latent value) + two likelihood warps in one block
+    out->reserved = 0;
     return DICEGP_OK;
 }
 
@@ -1253,7 +1259,7 @@ int dicegp_upload_genes(dicegp_ctx *c, int32_t G, int32_t T, const int32_t *n_is
     for (int g = 0; g < G; ++g) {
         const int C = n_iso[g];
         if (C < 1 || C > DG_MAXC) return c->fail(DICEGP_ERR_LIMIT, "upload_genes: isoform count outside [1, max_isoforms]");
-        if ((int64_t)C * T > DG_MAXCT) return c->fail(DICEGP_ERR_LIMIT, "upload_genes: C*T beyond the compiled limit");
+        if ((int64_t)C * T > DG_LB_THREADS - 64) return c->fail(DICEGP_ERR_LIMIT, "upload_genes: C*T beyond max_latent (dicegp_get_limits)");
         c->hwoff[g] = w; c->hlenoff[g] = l;
         int64_t r = 0;
         for (int t = 0; t < T; ++t) {
@@ -1700,15 +1706,12 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
         return c->fail(DICEGP_ERR_ARG, "posterior_summary: NULL or empty argument");
     DG_CUDA(c, cudaSetDevice(c->device));
     int64_t total = 0;
-    size_t smem = 0;
     for (int i = 0; i < n; ++i) {
         const int id = chain_ids[i];
         if (id < 0 || id >= c->n_chains) return c->fail(DICEGP_ERR_ARG, "posterior_summary: chain id out of range");
         const dicegp_chain_desc &d = c->hdesc[id];
         total = std::max<int64_t>(total, out_off[i] + (int64_t)c->hC[d.gene] * d.Tc);
-        smem = std::max(smem, (size_t)d.M * sizeof(unsigned long long));
     }
-    if (smem > c->smem_optin - 4096) return c->fail(DICEGP_ERR_LIMIT, "posterior_summary: M too large for the shared-memory radix select");
     // Launch groups by rows kept: the radix select holds one column in shared memory, so
     // short chains (the bulk) run 8 blocks per SM and only the long ones need a whole SM.
     std::vector<int32_t> ids(chain_ids, chain_ids + n), nr(n), mr(n);
@@ -1716,18 +1719,28 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
         int rc = dicegp_chain_status(c, n, ids.data(), mr.data(), nr.data(), nullptr, nullptr, nullptr);
         if (rc != DICEGP_OK) return rc;
     }
+    // classes 0-3 by rows written; class 4: chains that keep more rows after the burn-in than one column of
+    // keys fits shared memory (any --mcmc max_run works: those select in a global scratch row instead)
+    constexpr int kClasses = 5;
     const int bounds[4] = {3072, 7168, 14336, 0x7fffffff};
+    const int64_t smem_rows = (int64_t)(c->smem_optin - 4096) / (int64_t)sizeof(unsigned long long);
     std::vector<int32_t> order;            // positions grouped by size class
-    int gstart[5] = {0, 0, 0, 0, 0}, gmax[4] = {1, 1, 1, 1};
-    for (int k = 0; k < 4; ++k) {
+    int gstart[kClasses + 1] = {0, 0, 0, 0, 0, 0}, gmax[kClasses] = {1, 1, 1, 1, 1};
+    for (int k = 0; k < kClasses; ++k) {
         gstart[k] = (int)order.size();
         for (int i = 0; i < n; ++i) {
+            // the keys are the rows kept after the burn-in int(m/4) (run_utils.py:125)
+            const int keep = nr[i] - (mr[i] > 0 ? mr[i] >> 2 : 0);
+            const bool huge = keep > smem_rows;
             const int lo = k == 0 ? -1 : bounds[k - 1];
-            // shared memory holds the rows kept after the burn-in int(m/4) (run_utils.py:125)
-            if (nr[i] > lo && nr[i] <= bounds[k]) { order.push_back(i); gmax[k] = std::max(gmax[k], nr[i] - (mr[i] > 0 ? mr[i] >> 2 : 0)); }
+            const bool mine = k == 4 ? huge : (!huge && nr[i] > lo && nr[i] <= bounds[k]);
+            if (mine) { order.push_back(i); gmax[k] = std::max(gmax[k], keep); }
         }
     }
-    gstart[4] = (int)order.size();
+    gstart[kClasses] = (int)order.size();
+    const int n_huge = gstart[5] - gstart[4];
+    if (n_huge > 0 && c->skeys.resize((size_t)n_huge * gmax[4]) != cudaSuccess)
+        return c->fail(DICEGP_ERR_NOMEM, "posterior_summary: device allocation failed (select scratch)");
     std::vector<int32_t> ids_sorted(n);
     std::vector<int64_t> off_sorted(n);
     for (int i = 0; i < n; ++i) { ids_sorted[i] = chain_ids[order[i]]; off_sorted[i] = out_off[order[i]]; }
@@ -1750,14 +1763,15 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
         // DRAM traffic, but four columns of keys in shared memory leave too few blocks per SM; and
         // finishing a selection early once its bucket holds <= 32 keys -- no gain.)
         if ((e = cudaEventRecord(c->ev_fork, c->stream)) != cudaSuccess) break;
-        for (int k = 3; k >= 0 && e == cudaSuccess; --k) {
+        for (int k = kClasses - 1; k >= 0 && e == cudaSuccess; --k) {
             const int cnt = gstart[k + 1] - gstart[k];
             if (cnt == 0) continue;
-            const size_t sm = (size_t)gmax[k] * sizeof(unsigned long long);
+            const size_t sm = k == 4 ? 0 : (size_t)gmax[k] * sizeof(unsigned long long);
             cudaStream_t st = c->class_stream[k];
             if ((e = cudaStreamWaitEvent(st, c->ev_fork, 0)) != cudaSuccess) break;
             dicegp_summary_kernel<<<cnt, DG_SUM_THREADS, sm, st>>>(make_gene_tab(c), make_chain_tab(c), dids.p + gstart[k],
-                                                                   dmean.p, dci.p, doff.p + gstart[k], dlik.p + gstart[k]);
+                                                                   dmean.p, dci.p, doff.p + gstart[k], dlik.p + gstart[k],
+                                                                   k == 4 ? c->skeys.p : nullptr, (size_t)gmax[4]);
             ++c->total_launches;
             if ((e = cudaGetLastError()) != cudaSuccess) break;
             if ((e = cudaEventRecord(c->ev_join[k], st)) != cudaSuccess) break;

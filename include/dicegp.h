@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DICEGP_ABI_VERSION 1
+#define DICEGP_ABI_VERSION 2
 
 typedef struct dicegp_ctx dicegp_ctx;
 
@@ -51,6 +51,9 @@ typedef struct dicegp_limits {
     int32_t max_times;       /* T  */
     int32_t abi_version;
     int32_t sm_count;        /* of the device behind the handle */
+    int32_t max_latent;      /* C * T of one gene: every latent value has its own thread in the state
+                                warps of a chain's block; what dicegp_upload_genes accepts runs */
+    int32_t reserved;
 } dicegp_limits;
 
 /* Chain state codes reported by dicegp_chain_status. */

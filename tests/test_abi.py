@@ -28,7 +28,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.dicegp_abi_version() == 1
+    assert lib.dicegp_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_chain_desc_layout():

@@ -120,6 +120,27 @@ def test_device_summary_matches_numpy(sampler):
         assert abs(r.lik_marg - lik_marg) <= 1e-13 * abs(lik_marg)
 
 
+def test_summary_of_chains_longer_than_shared_memory():
+    """`--mcmc 0 50000 ...`: a chain that keeps more rows after the burn-in than one column of keys fits
+    shared memory (about 28.5k) is summarised through a global scratch row: same bit-exact mean /
+    order statistics (the reference accepts any max_run)."""
+    genes = [97, 98]
+    packed = _batch("static", genes, reads=60)
+    s = BatchSampler(0)
+    try:
+        res = s.run(packed, M=50000, initial=50000, gap=1000, seed=3, gene_ids=genes, keep_trace=True)
+        for r in res:
+            Psi, Y, Pro, Lik = r.trace
+            assert r.m == 49999 and len(Lik) == 50000
+            psi_mean, psi_95, lik_marg, _ = orc.posterior_summary(Psi, Y, Lik, r.m)
+            assert np.array_equal(r.psi_mean, psi_mean)
+            for c in range(Psi.shape[1]):
+                assert np.array_equal(r.psi_95[c], psi_95[c])
+            assert abs(r.lik_marg - lik_marg) <= 1e-13 * abs(lik_marg)
+    finally:
+        s.close()
+
+
 def test_trace_pool_grows_and_reports_exhaustion():
     """Chains longer than their first page allocate pages on the device; a pool that is too
     small stops the chain with CHAIN_NOMEM instead of corrupting memory."""
