@@ -8,7 +8,6 @@ pool, `-p`), (2) GPU: all multi-isoform genes sampled in batches by `BatchSample
 
 Differences, all deliberate: single-isoform genes get psi = 1 rows instead of crashing the
 worker; `.sample.gz` is written in text mode (Appendix B #11);
-`--bias` modes other than `unif` are refused (they need a reference FASTA and a bias file);
 `--thetas x learn` runs host-driven chains, one gene at a time, with the likelihood on the GPU
 (theta2_mode.py) and -- like the reference's sampler -- only handles two-isoform genes;
 genes beyond the library's shape limits (isoforms, isoforms x time points) are named and skipped;
@@ -58,8 +57,9 @@ def build_parser():
                      help="Four arguments for in MCMC iterations: save_sample,max_run,min_run,gap_run. "
                           "[default: 0 20000 1000 100]")
     group.add_option("--device", type="int", dest="device", default=0, help="GPU index (first GPU with --gpus) [default: %default]")
-    group.add_option("--gpus", type="int", dest="gpus", default=1,
-                     help="GPUs of this box to shard the genes over (read-count-balanced greedy partition) [default: %default]")
+    group.add_option("--gpus", dest="gpus", default="1",
+                     help="GPUs of this box to shard the genes over (read-count-balanced greedy partition): a count N "
+                          "(devices --device .. --device+N-1) or a comma-separated list of device indices [default: %default]")
     group.add_option("--seed", type="int", dest="seed", default=0, help="seed of the device random stream")
     group.add_option("--batch", type="int", dest="batch", default=20000, help="genes per GPU batch")
     parser.add_option_group(group)
@@ -67,8 +67,8 @@ def build_parser():
 
 
 def _inputs_worker(args):
-    gene, sam_list, FLmean, FLstd = args
-    return gene_inputs(gene, sam_list, FLmean, FLstd)
+    gene, sam_list, FLmean, FLstd, bias_mode, ref_file, bias_file = args
+    return gene_inputs(gene, sam_list, FLmean, FLstd, bias_mode, ref_file, bias_file)
 
 
 def sample_genes(idx, gene_inputs_list, device, batch, sample_num, run_kw, progress=None):
@@ -164,9 +164,26 @@ def main(argv=None):
         theta2 = None                                                # diceseq.py:170-171
     else:
         theta2 = max(0.00001, float(theta2))
-    if options.bias_args[0] != "unif":
-        print("[DICEseq] Error: only --bias unif is supported (bias modes need a reference FASTA and bias file).")
-        sys.exit(1)
+    bias_mode, ref_file, bias_file = options.bias_args               # diceseq.py:175-190
+    if bias_mode == "unif":
+        ref_file = bias_file = None
+    elif ref_file == "None":
+        print("[DICEseq] No reference sequence, change to uniform mode.")
+        ref_file = bias_file = None
+        bias_mode = "unif"
+    elif bias_file == "None":
+        print("[DICEseq] No bias parameter file, change to uniform mode.")
+        ref_file = bias_file = None
+        bias_mode = "unif"
+    else:
+        if bias_mode not in ("end5", "end3", "both"):
+            print("[DICEseq] Error: --bias mode must be unif, end5, end3 or both.")
+            sys.exit(1)
+        bias_file = bias_file.split("---")
+        for f in [ref_file] + bias_file:
+            if not os.path.isfile(f):
+                print("Error: No such file\n    -- %s" % f)
+                sys.exit(1)
 
     if options.add_premRNA:
         for g in genes:
@@ -177,7 +194,7 @@ def main(argv=None):
         len(genes), options.device, options.nproc))
 
     # ---- stage 1: host matrices -------------------------------------------------------------
-    jobs = [(g, sam_list, FLmean, FLstd) for g in genes]
+    jobs = [(g, sam_list, FLmean, FLstd, bias_mode, ref_file, bias_file) for g in genes]
     if options.nproc <= 1 or len(genes) < 4:
         inputs = [_inputs_worker(j) for j in jobs]
     else:
@@ -228,12 +245,14 @@ def main(argv=None):
         multi = [i for i in multi if i not in drop]
 
     run_kw = dict(X=X, theta1=theta1, theta2=theta2, M=Mmax, initial=Mmin, gap=Mgap, seed=options.seed)
-    n_gpus = max(1, int(options.gpus))
+    devices = ([int(d) for d in str(options.gpus).split(",")] if "," in str(options.gpus)
+               else [options.device + r for r in range(max(1, int(options.gpus)))])
+    n_gpus = len(devices)
     if n_gpus == 1 or len(multi) < 2 * n_gpus:
         def progress(done):
             sys.stdout.write("\r[DICEseq] %d / %d genes sampled in %.1f sec." % (done, len(multi), time.time() - start_time))
             sys.stdout.flush()
-        res_d, samp_d = sample_genes(multi, [inputs[i] for i in multi], options.device, options.batch, sample_num, run_kw, progress)
+        res_d, samp_d = sample_genes(multi, [inputs[i] for i in multi], devices[0], options.batch, sample_num, run_kw, progress)
         results.update(res_d)
         samples.update(samp_d)
     elif multi:
@@ -246,14 +265,14 @@ def main(argv=None):
         ctx = multiprocessing.get_context("spawn")
         with ctx.Pool(n_gpus) as pool:
             jobs2 = [pool.apply_async(sample_genes, ([multi[k] for k in b], [inputs[multi[k]] for k in b],
-                                                     options.device + r, options.batch, sample_num, run_kw))
+                                                     devices[r], options.batch, sample_num, run_kw))
                      for r, b in enumerate(bins)]
             for r, j in enumerate(jobs2):
                 res_d, samp_d = j.get()
                 results.update(res_d)
                 samples.update(samp_d)
                 sys.stdout.write("\r[DICEseq] GPU %d done: %d / %d genes sampled in %.1f sec." % (
-                    options.device + r, len(results), len(multi), time.time() - start_time))
+                    devices[r], len(results), len(multi), time.time() - start_time))
                 sys.stdout.flush()
 
     # ---- stage 3: output, in annotation order -----------------------------------------------

@@ -15,13 +15,47 @@ from .bam import load_samfile
 from .read_model import gene_time_matrices
 
 
-def gene_inputs(gene, sam_list, FLmean=None, FLstd=None):
+_FASTA_CACHE, _BIAS_CACHE = {}, {}
+
+
+def _fasta(path):
+    from .bias import FastaFile
+    if path not in _FASTA_CACHE:
+        _FASTA_CACHE[path] = FastaFile(path)
+    return _FASTA_CACHE[path]
+
+
+def _bias(path):
+    from .bias import BiasFile
+    if path not in _BIAS_CACHE:
+        _BIAS_CACHE[path] = BiasFile(path)
+    return _BIAS_CACHE[path]
+
+
+def gene_inputs(gene, sam_list, FLmean=None, FLstd=None, bias_mode="unif", ref_file=None, bias_file=None):
     """R_all, len_iso_all, prob_iso_all (lists over time points) and count (T,) of one gene.
-    `sam_list[t]` lists the replicate BAM files of time point t.  Uniform model, single-mate
-    mode: the two settings the reference CLI hard-codes (diceseq.py:150-153)."""
+    `sam_list[t]` lists the replicate BAM files of time point t.  Single-mate mode (diceseq.py:152).
+    bias_mode unif -> proU; end5 / end3 / both -> proB with the sequence weights of `bias_file` (a list: one
+    file for all time points or one per time point) on the genome `ref_file`; the fragment-length model
+    takes the bias file's mean / std once a file provides them, and keeps them for the later time points
+    (run_utils.py:66-77).  The effective length stays efflen_unif in every mode (run_utils.py:86)."""
     R_all, len_all, prob_all, count = [], [], [], []
-    for files in sam_list:
-        R, P, L, n = gene_time_matrices(gene, [load_samfile(f) for f in files], FLmean, FLstd)
+    for i, files in enumerate(sam_list):
+        bias = None
+        if bias_mode != "unif":
+            if len(bias_file) == len(sam_list):
+                bias = _bias(bias_file[i])
+            elif len(bias_file) == 1:
+                bias = _bias(bias_file[0])
+            if bias is not None:
+                if FLmean is None and bias.flen_mean != 0:
+                    FLmean = bias.flen_mean
+                if FLstd is None and bias.flen_std != 0:
+                    FLstd = bias.flen_std
+        if bias_mode != "unif" and bias is None:
+            raise ValueError("--bias: give one bias file, or one per time point")
+        R, P, L, n = gene_time_matrices(gene, [load_samfile(f) for f in files], FLmean, FLstd, bias_mode,
+                                        _fasta(ref_file) if bias_mode != "unif" else None, bias)
         R_all.append(R)
         len_all.append(L)
         prob_all.append(P)

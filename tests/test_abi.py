@@ -28,7 +28,9 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version(lib):
+    from diceseq_b200 import _lib
     assert lib.dicegp_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.shape_limits() == {"max_isoforms": 32, "max_times": 32, "max_latent": 448}
 
 
 def test_chain_desc_layout():

@@ -89,6 +89,44 @@ def test_cli_in_several_batches_gives_the_same_file(tmp_path):
     assert outs[0] == outs[1]
 
 
+def test_cli_sharded_over_two_workers_gives_the_same_file(tmp_path):
+    """--gpus: the genes are LPT-partitioned over one worker process per listed device and gathered; the
+    random streams are keyed by the annotation index of the gene, so the .dice file is byte-identical to the
+    single-process run (two workers share device 0 here: the test box has one GPU)."""
+    from diceseq_b200 import cli
+    sams = "---".join(os.path.join(DATA, "reads_t%d.sorted.bam" % t) for t in (1, 2, 3))
+    base = ["-a", os.path.join(DATA, "yeast_RNA_splicing.gtf"), "-s", sams, "-p", "1", "--add_premRNA", "--time_seq=1.5,2.5,5"]
+    cli.main(base + ["-o", str(tmp_path / "one")])
+    cli.main(base + ["-o", str(tmp_path / "two"), "--gpus", "0,0"])
+    assert open(str(tmp_path / "one.dice")).read() == open(str(tmp_path / "two.dice")).read()
+
+
+def test_bias_mode_from_the_command_line(tmp_path):
+    """--bias both REF BIAS: the bias-weighted read probabilities (read_model.py, bit-identical to the
+    reference's on this data: tests/test_host_pipeline.py) go through the same sampler; the file has the same
+    shape as the uniform run, valid ratios and intervals, and estimates that differ from the uniform ones."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import synth_fasta
+    from diceseq_b200 import cli
+    from diceseq_b200.annotation import loadgene
+    fa = str(tmp_path / "genome.fa")
+    synth_fasta.write_fasta(synth_fasta.genome_for(loadgene(os.path.join(DATA, "yeast_RNA_splicing.gtf"))), fa)
+    sams = "---".join(os.path.join(DATA, "reads_t%d.sorted.bam" % t) for t in (1, 2, 3))
+    base = ["-a", os.path.join(DATA, "yeast_RNA_splicing.gtf"), "-s", sams, "-p", "1", "--add_premRNA", "--time_seq=1.5,2.5,5"]
+    cli.main(base + ["-o", str(tmp_path / "unif")])
+    cli.main(base + ["-o", str(tmp_path / "both"), "--bias", "both", fa, os.path.join(DATA, "yeast_4tU.bias")])
+    h1, r1 = _read_dice(str(tmp_path / "unif.dice"))
+    h2, r2 = _read_dice(str(tmp_path / "both.dice"))
+    assert h1 == h2 and [r[:2] + [r[3]] for r in r1] == [r[:2] + [r[3]] for r in r2]
+    a = np.array([r[4:] for r in r1], float).reshape(len(r1), -1, 4)
+    b = np.array([r[4:] for r in r2], float).reshape(len(r2), -1, 4)
+    assert ((b[:, :, 1] >= 0) & (b[:, :, 1] <= 1)).all()
+    assert (b[:, :, 2] <= b[:, :, 1] + 1e-9).all() and (b[:, :, 1] <= b[:, :, 3] + 1e-9).all()
+    assert np.abs(b[0::2, :, 1] + b[1::2, :, 1] - 1).max() < 0.006         # two isoforms per gene, printed with 3 digits
+    assert not np.array_equal(a[:, :, 1], b[:, :, 1])                    # the weights do move the estimates
+
+
 def test_theta2_sampling_mode_from_the_command_line(tmp_path):
     """`--thetas 3 learn` (diceseq.py:170-171): every gene's chains sample theta2 too; host-driven
     steps with the likelihood on the GPU.  The demo genes have two isoforms each (with pre-mRNA),

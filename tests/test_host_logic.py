@@ -135,3 +135,18 @@ def test_truncated_normal_density_and_erf_approximation():
     xs = np.linspace(0.2, 3.0, 20001)
     dens = np.exp([trun_normal_logpdf(x, 1.0, 0.7, 0.2, 3.0) for x in xs])
     assert abs(np.trapezoid(dens, xs) - 1.0) < 1e-5
+
+
+def test_diceseq_import_shim_exports_the_reference_names():
+    """`import diceseq` (diceseq/__init__.py:4-16 of the reference): the names this repository implements
+    resolve, `diceseq.diceseq.main` is the command line, the others fail with a clear ImportError."""
+    import diceseq
+    import diceseq.diceseq as entry
+    import diceseq_b200
+    assert diceseq.Psi_GP_MH is diceseq_b200.Psi_GP_MH and diceseq.GP_K is diceseq_b200.GP_K
+    for name in ("normal_pdf", "Geweke_Z", "Gene", "Transcript", "loadgene", "load_annotation", "load_samfile",
+                 "fetch_reads", "TranSplice", "FastaFile", "BiasFile", "__version__"):
+        assert hasattr(diceseq, name), name
+    assert callable(entry.main) and entry.build_parser().has_option("--bias")
+    with pytest.raises(ImportError):
+        diceseq.miso_BF

@@ -56,6 +56,64 @@ def test_read_model_matches_reference_bit_for_bit():
             assert np.array_equal(L, z[k + "_efflen"]) and cnt == int(z[k + "_count"]), k
 
 
+def test_bias_mode_read_model_matches_reference_bit_for_bit(tmp_path):
+    """end5 / end3 / both: proB and the bias-weighted effective lengths against the unmodified reference's
+    TranSplice (set_sequence + set_bias("seq") + get_ready, tests/golden/make_golden_host_bias.py) on the
+    bundled reads, the bundled bias file and the seeded synthetic genome."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import synth_fasta
+    from diceseq_b200.bias import BiasFile, FastaFile
+    z = np.load(os.path.join(ROOT, "tests", "golden", "host_matrices_bias.npz"))
+    genes = loadgene(os.path.join(DATA, "yeast_RNA_splicing.gtf"))
+    fa = str(tmp_path / "genome.fa")
+    synth_fasta.write_fasta(synth_fasta.genome_for(genes), fa)
+    fasta, bias = FastaFile(fa), BiasFile(os.path.join(DATA, "yeast_4tU.bias"))
+    for g in genes:
+        g.add_premRNA()
+        for ti in (1, 3):
+            bam = load_samfile(os.path.join(DATA, "reads_t%d.sorted.bam" % ti))
+            for mode in ("end5", "end3", "both"):
+                R, P, L, cnt, Lb = gene_time_matrices(g, [bam], None, None, mode, fasta, bias, with_efflen_bias=True)
+                k = "%s_t%d_%s" % (g.geneID, ti, mode)
+                assert np.array_equal(R, z[k + "_R"]), k
+                assert np.array_equal(P, z[k + "_proB"], equal_nan=True), k
+                assert np.array_equal(Lb, z[k + "_efflen_bias"]), k
+                assert np.array_equal(L, z[k + "_efflen_unif"]), k
+    g = [x for x in genes if x.geneID == str(z["flen_case_gene"])][0]
+    mu, sd = z["flen_mean_std"]
+    assert (bias.flen_mean, bias.flen_std) == (mu, sd)
+    R, P, L, cnt, Lb = gene_time_matrices(g, [load_samfile(os.path.join(DATA, "reads_t2.sorted.bam"))], mu, sd, "both",
+                                          fasta, bias, with_efflen_bias=True)
+    assert np.array_equal(P, z["flen_case_proB"], equal_nan=True) and np.array_equal(Lb, z["flen_case_efflen_bias"])
+
+
+def test_gene_inputs_in_bias_mode_follows_get_psi(tmp_path):
+    """run_utils.py:66-87: one bias file for all time points (or one per time point); the fragment-length
+    model takes the file's mean / std; the effective length stays the uniform one."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import synth_fasta
+    from diceseq_b200.bias import BiasFile, FastaFile
+    genes = loadgene(os.path.join(DATA, "yeast_RNA_splicing.gtf"))
+    fa = str(tmp_path / "genome.fa")
+    synth_fasta.write_fasta(synth_fasta.genome_for(genes), fa)
+    bf = os.path.join(DATA, "yeast_4tU.bias")
+    g = genes[2]
+    g.add_premRNA()
+    f1, f3 = (os.path.join(DATA, "reads_t%d.sorted.bam" % t) for t in (1, 3))
+    R_all, L_all, P_all, count = gene_inputs(g, [[f1], [f3]], None, None, "end5", fa, [bf])
+    bias = BiasFile(bf)
+    for t, f in enumerate((f1, f3)):
+        R, P, L, n = gene_time_matrices(g, [load_samfile(f)], bias.flen_mean, bias.flen_std, "end5", FastaFile(fa), bias)
+        assert np.array_equal(R_all[t], R) and np.array_equal(P_all[t], P, equal_nan=True)
+        assert np.array_equal(L_all[t], [tr.tranL for tr in g.trans]) and count[t] == n
+    two = gene_inputs(g, [[f1], [f3]], None, None, "end5", fa, [bf, bf])
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(two[2], P_all))
+    with pytest.raises(ValueError):
+        gene_inputs(g, [[f1], [f3]], None, None, "end5", fa, [bf, bf, bf])
+
+
 def test_replicates_concatenate():
     genes = loadgene(os.path.join(DATA, "yeast_RNA_splicing.gtf"))
     g = genes[1]
