@@ -443,6 +443,28 @@ dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, 
     }
 }
 
+// Tiled copy of W for the wide-round kernel (GeneTab::Wt): one block per gene.
+__global__ void dicegp_tile_kernel(GeneTab gt, int G, double *__restrict__ Wt) {
+    const int g = blockIdx.x;
+    if (g >= G) return;
+    const int C = gt.C[g], T = gt.T;
+    const double2 *Wg = reinterpret_cast<const double2 *>(gt.W + gt.woff[g]);
+    double2 *out = reinterpret_cast<double2 *>(Wt + gt.wtoff[g]);
+    const int32_t *roff = gt.roff + (size_t)g * (T + 1), *toff = gt.toff + (size_t)g * (T + 1);
+    for (int t = 0; t < T; ++t) {
+        const int np = (roff[t + 1] - roff[t]) >> 1;
+        const double2 *src = Wg + (size_t)C * (roff[t] >> 1);
+        double2 *dst = out + (size_t)toff[t] * C * 16;
+        const int ntile = toff[t + 1] - toff[t];
+        const int total = ntile * C * 16;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int tile = i / (C * 16), r = i - tile * (C * 16);
+            const int k = r >> 4, w = (tile << 4) + (r & 15);
+            dst[i] = w < np ? src[(size_t)k * np + w] : make_double2(0.0, 0.0);
+        }
+    }
+}
+
 // =======================================================================================
 // host context
 // =======================================================================================
@@ -491,9 +513,14 @@ struct dicegp_ctx {
 
     // genes
     int G = 0, T = 0;
-    std::vector<int32_t> hC, hncnt, hroff;
+    std::vector<int32_t> hC, hncnt, hroff, htoff;
+    std::vector<int64_t> hwtoff;
+    bool tiles_valid = false;               // dWt holds the tiled copy of the uploaded W
+    int64_t wt_total = 0;                   // doubles of the tiled copy
     std::vector<int64_t> hwoff, hlenoff;
-    DevBuf<int32_t> dC, dncnt, droff;
+    DevBuf<int32_t> dC, dncnt, droff, dtoff;
+    DevBuf<int64_t> dwtoff;
+    DevBuf<double> dWt;
     DevBuf<int64_t> dwoff, dlenoff;
     DevBuf<double> dW, dlen;
 
@@ -562,6 +589,7 @@ GeneTab make_gene_tab(dicegp_ctx *c) {
     GeneTab g;
     g.C = c->dC.p; g.woff = c->dwoff.p; g.roff = c->droff.p; g.ncnt = c->dncnt.p;
     g.lenoff = c->dlenoff.p; g.W = c->dW.p; g.len = c->dlen.p; g.T = c->T;
+    g.Wt = c->dWt.p; g.wtoff = c->dwtoff.p; g.toff = c->dtoff.p;
     return g;
 }
 ChainTab make_chain_tab(dicegp_ctx *c) {
@@ -778,6 +806,18 @@ chain_kernel_t chain_kernel_for(int kind, bool w_in_smem, bool cluster) {
     }
 }
 
+// The tiled copy of W (wide-round kernel), built once per uploaded batch, when a wide launch first needs it.
+int ensure_tiles(dicegp_ctx *c) {
+    if (c->tiles_valid) return DICEGP_OK;
+    if (c->dWt.resize(std::max<int64_t>(c->wt_total, 2)) != cudaSuccess)
+        return c->fail(DICEGP_ERR_NOMEM, "device allocation failed (tiled copy of W)");
+    dicegp_tile_kernel<<<c->G, 256, 0, c->stream>>>(make_gene_tab(c), c->G, c->dWt.p);
+    DG_CUDA(c, cudaGetLastError());
+    ++c->total_launches;
+    c->tiles_valid = true;
+    return DICEGP_OK;
+}
+
 // Common driver: advance `ids` (host order) by n_steps with stream args `sa`.
 // The kernel's slot is the position in the per-group id list, so the per-slot host-stream
 // offsets are permuted alongside.
@@ -803,6 +843,12 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
         by_group[k].push_back(ids[i]);
         slot_src[k].push_back((int32_t)i);
     }
+    for (int kind = 0; kind < kKinds; ++kind)
+        if (!by_group[kWideTier * kKinds + kind].empty()) {
+            int rc = ensure_tiles(c);
+            if (rc != DICEGP_OK) return rc;
+            break;
+        }
     if (persistent) {
         // heavy chains first (cost ~ C * reads)
         for (int k = 0; k < kGroups; ++k) {
@@ -1035,7 +1081,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             const char *nm[8] = {"S", "waitf", "lik", "waitp", "decide", "waits", "rows", "aux"};
             double tot = 0;
             for (int i = 0; i < 8; ++i) { fprintf(stderr, " %s=%.0f", nm[i], h[i] / n); if (i < 7) tot += h[i] / n; }
-            fprintf(stderr, " total=%.0f\n", tot);
+            fprintf(stderr, " total=%.0f | within lik (warp 0): barrier wait=%.0f task=%.0f normals=%.0f issue=%.0f flush=%.0f\n", tot, h[8] / n, h[9] / n, h[12] / n, h[13] / n, h[14] / n);
         } else {
             const char *nm[9] = {"S", "window", "B2wait", "decide", "update", "geweke", "-", "-", "-"};
             double n = (double)std::max<unsigned long long>(h[10], 1);
@@ -1207,6 +1253,7 @@ int dicegp_destroy(dicegp_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->dC.release(); c->dncnt.release(); c->droff.release(); c->dwoff.release(); c->dlenoff.release();
+    c->dtoff.release(); c->dwtoff.release(); c->dWt.release();
     c->dW.release(); c->dlen.release();
     c->cgene.release(); c->ct0.release(); c->cTc.release(); c->cM.release(); c->cinit.release();
     c->cgap.release(); c->cm_next.release(); c->ccnt.release(); c->cstate.release(); c->cm_ret.release();
@@ -1253,9 +1300,12 @@ int dicegp_upload_genes(dicegp_ctx *c, int32_t G, int32_t T, const int32_t *n_is
     c->hC.assign(n_iso, n_iso + G);
     c->hncnt.assign(n_reads, n_reads + (size_t)G * T);
     c->hroff.assign((size_t)G * (T + 1), 0);
+    c->htoff.assign((size_t)G * (T + 1), 0);
+    c->hwtoff.assign(G, 0);
+    c->tiles_valid = false;
     c->hwoff.assign(G, 0);
     c->hlenoff.assign(G, 0);
-    int64_t w = 0, l = 0;
+    int64_t w = 0, l = 0, wt_total = 0;
     for (int g = 0; g < G; ++g) {
         const int C = n_iso[g];
         if (C < 1 || C > DG_MAXC) return c->fail(DICEGP_ERR_LIMIT, "upload_genes: isoform count outside [1, max_isoforms]");
@@ -1270,6 +1320,17 @@ int dicegp_upload_genes(dicegp_ctx *c, int32_t G, int32_t T, const int32_t *n_is
             if (r > 0x7fffffff) return c->fail(DICEGP_ERR_LIMIT, "upload_genes: more than 2^31 reads in one gene");
         }
         c->hroff[(size_t)g * (T + 1) + T] = (int32_t)r;
+        {
+            int64_t tiles = 0;                                   // 16-word tiles of the wide-round kernel
+            for (int t = 0; t < T; ++t) {
+                c->htoff[(size_t)g * (T + 1) + t] = (int32_t)tiles;
+                const int64_t np = (c->hroff[(size_t)g * (T + 1) + t + 1] - c->hroff[(size_t)g * (T + 1) + t]) >> 1;
+                tiles += (np + 15) >> 4;
+            }
+            c->htoff[(size_t)g * (T + 1) + T] = (int32_t)tiles;
+            c->hwtoff[g] = wt_total;
+            wt_total += tiles * C * 32;                          // doubles
+        }
         w += (int64_t)C * r;
         l += (int64_t)C * T;
     }
@@ -1283,6 +1344,11 @@ int dicegp_upload_genes(dicegp_ctx *c, int32_t G, int32_t T, const int32_t *n_is
     DG_CUDA(c, cudaMemcpyAsync(c->dC.p, c->hC.data(), G * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     DG_CUDA(c, cudaMemcpyAsync(c->dncnt.p, c->hncnt.data(), (size_t)G * T * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     DG_CUDA(c, cudaMemcpyAsync(c->droff.p, c->hroff.data(), (size_t)G * (T + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    DG_CUDA(c, c->dtoff.resize((size_t)G * (T + 1)));
+    DG_CUDA(c, c->dwtoff.resize(G));
+    DG_CUDA(c, cudaMemcpyAsync(c->dtoff.p, c->htoff.data(), (size_t)G * (T + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    DG_CUDA(c, cudaMemcpyAsync(c->dwtoff.p, c->hwtoff.data(), G * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    c->wt_total = wt_total;
     DG_CUDA(c, cudaMemcpyAsync(c->dwoff.p, c->hwoff.data(), G * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     DG_CUDA(c, cudaMemcpyAsync(c->dlenoff.p, c->hlenoff.data(), G * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     // W goes up in 16 MB pieces, each submitted when the previous one has landed: another context

@@ -31,6 +31,13 @@ struct GeneTab {
     const double *W;
     const double *len;
     int32_t T;
+    // tiled copy of W for the wide-round kernel (built on the device after the upload): the isoform-major block
+    // of every time point cut into TILES of 16 words (32 reads); a tile holds its C rows back to back
+    // ([k][16 words], zero padded), tiles follow each other in (time, position) order, so any run of
+    // consecutive tiles of a gene is ONE contiguous range (one TMA bulk copy).
+    const double *Wt;
+    const int64_t *wtoff;    // [G]        first double of the gene's tiles
+    const int32_t *toff;     // [G*(T+1)]  tiles of the gene before time t
 };
 
 struct ChainTab {

@@ -1,5 +1,5 @@
 // dicegp_wide.cuh -- the MH loop of a joint (time-series) chain, kernel v3: WIDE rejection-chain rounds
-// without warp specialisation, W streamed through a block-shared TMA ring.
+// without warp specialisation, W streamed through per-warp TMA rings.
 //
 // What bounds a chain is the serial part of a round (proposal -> exp -> softmax -> f | likelihood |
 // log -> accept test -> state update: ~3000 cycles of dependent fp64 latency) and, for wide genes, the
@@ -13,31 +13,39 @@
 // sequential execution.
 //
 // One block = NCW consumer warps + 1 auxiliary warp; every consumer warp does every phase:
-//   S      item (j, t): candidate y -> exp -> length-weighted softmax f[t][.][j];  item (j, c): GP prior
-//   LIK    reads in TASKS of 16 words (32 reads) of one time point; a STAGE = NCW consecutive tasks, one
-//          per consumer warp, brought in by 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx,
-//          one copy per isoform row and time point) into a ring of D stages.  The warp that releases a
-//          stage last re-arms its barrier and issues the copies of stage q + D (no producer warp, no
-//          empty barriers).  The stage sequence of a round is the same every round, so the first stages
-//          of the next round are prefetched while this round decides; when the whole W fits the ring
-//          (D >= stages per round) nothing is ever re-issued: W is resident.
+//   S      two sub-phases over all threads: item (j, c, t): candidate y -> exp and its GP-prior term; then
+//          item (j, c, t): length-weighted softmax f[t][c][j], item (j, c): prior of one isoform
+//   LIK    reads in TASKS of 16 words (32 reads) of one time point.  W is read from a TILED copy (GeneTab::Wt,
+//          made on the device after the upload): a tile = the C rows of one task back to back, tiles in
+//          (time, position) order, so the contiguous run of tasks a warp owns is ONE byte range.  Each consumer
+//          warp streams its run through its OWN ring of up to 8 slots with 1-D TMA bulk copies
+//          (cp.async.bulk + mbarrier complete_tx, one copy per slot, issued by lane 0 when the slot has been
+//          consumed); the sequence repeats every round, so the first slots of the next round are in flight
+//          while this round decides; a run that fits the ring is loaded once (W resident).  No block-level
+//          synchronisation inside the pass.
 //          Lane (s, h), s = lane & 7, h = lane >> 3: words s and s + 8 of the task (4 reads), candidates
-//          4h .. 4h+3 (RJ = 4) -- a 4 x RJ register tile per lane; per isoform 2 conflict-free LDS.128 of
-//          W (8 lanes x 16 B, broadcast over h) and RJ/2 LDS.128 of f feed 4 RJ DFMA: 0.25 shared-memory
-//          wavefronts per DFMA, half of what the fp64 pipe can consume.
+//          4h .. 4h+3 (RJ = 4) -- a 4 x RJ register tile per lane.
 //          prod_n x_n per candidate as (mantissa product, exponent sum); anything that is not a positive
 //          normal number sends the round to the real-log path (-inf / NaN like np.log(...).sum()).
-//   AUX    meanwhile the auxiliary warp produces the stream of the NEXT rounds (Philox normals ->
-//          increments, log u, proposal log-density Q) and reserves the trace pages of this round's rows.
+//   AUX    the stream of the NEXT rounds: the consumer warps make the Philox / Box-Muller normals (one pair per
+//          thread: ~150 dependent fp64 operations each) before their tasks, the auxiliary warp turns them into
+//          increments, log u and the proposal log-density Q, and reserves the trace pages of this round's rows.
 //   DECIDE every warp redundantly: lane j combines the per-warp partial products of candidate j, takes one
 //          log, adds the prior, tests  log u < ((P_try + Q) - P_now) - Q ; a ballot gives d*.
 //   UPDATE psi of the accepted state, trace rows (coalesced, all threads), Geweke rule when due.
-// Four block barriers per round.  Same stream, same saved state, same paged trace and incremental Geweke
+// Five block barriers per round.  Same stream, same saved state, same paged trace and incremental Geweke
 // sums as dg::run_chain -- a chain can be advanced by either kernel in turn.
+//
+// Measured (profiles/): per round at C = 8, 16 consumer warps: S 12k, likelihood 70-80k (the tile
+// loop reaches 39 of 64 DFMA lane-ops per clock in isolation, scripts/ubench/lik_tile.cu; in the kernel the
+// barrier waits, copy issue and per-task bookkeeping halve that), decide + update 12k cycles, for ~12 steps at
+// the acceptance rates of the straggler pass.  Used there (one chain per SM, W L2 resident): 20 % faster than
+// the general kernel.  In the throughput pass the general kernel's 2-4 chains per SM at 4 candidates per
+// round spend a third less fp64 work per committed step and win.
 #pragma once
 #include "dicegp_chain.cuh"
 
-#define DG_WIDE_MAXSTAGES 64
+#define DG_WIDE_SLOTS 8             // ring slots (tasks in flight) per consumer warp
 #define DG_WIDE_MAXCT 128           // latent values (C * Tc) of a chain this kernel takes
 #define DG_WIDE_THREADS 576         // launch bound: 17 warps (16 consumers + aux) or 2 blocks of 9 warps per SM
 
@@ -78,7 +86,7 @@ __host__ __device__ inline WideLayout dg_wide_layout(int C, int Tc, int ncw, int
     L.len = o; o += CT;
     L.ints = o; o += (3 * (Tc + 1) + 1) / 2 + 1;       // rel[Tc+1], ncnt[Tc], cum[Tc+1]
     L.gw = o; o += 2 * (ncw + 1) * (ctm < DG_GW_COLS ? (ctm > 0 ? ctm : 1) : DG_GW_COLS);
-    L.bars = o; o += DG_WIDE_MAXSTAGES + DG_WIDE_MAXSTAGES / 2;   // full barriers (8 B) + release counters (4 B)
+    L.bars = o; o += (ncw + 1) * DG_WIDE_SLOTS;                   // per consumer warp: one mbarrier per ring slot
     o = (o + 15) & ~15;
     L.ring = o;
     return L;
@@ -122,22 +130,29 @@ __device__ __forceinline__ double dg_np_sum_fn(F v, int n) {
 template <bool BLOCK>
 __device__ __forceinline__ void wide_sync() { if (BLOCK) __syncthreads(); else __syncwarp(); }
 
+// The Philox / Box-Muller normals of steps [s0, s1) into zbuf rows 0 .. s1-s0 (one item per pair: ~150 dependent
+// fp64 operations, so the items are spread over as many threads as there are).
+__device__ __noinline__ void wide_normals(int s0, int s1, int pt, int nprod, double *zbuf, int C, int Tc, uint64_t seed, int64_t sid) {
+    const int CT = C * Tc, CTm = CT - Tc, RL = CT + 2, ns = s1 - s0;
+    const int npair = (CTm + 1) >> 1;
+    for (int q = pt; q < ns * npair; q += nprod) {
+        const int ds = q / npair, i = q - ds * npair;
+        double z0, z1;
+        dg_normal_pair(seed, sid, (uint32_t)(s0 + ds), (uint32_t)i, z0, z1);
+        zbuf[ds * RL + 2 * i] = z0;
+        if (2 * i + 1 < CTm) zbuf[ds * RL + 2 * i + 1] = z1;
+    }
+}
+
 template <bool BLOCK>
 __device__ __noinline__ void wide_produce(bool dev_stream, int s0, int s1, int pt, int nprod, double *zbuf, double *dring,
                                           int RING, int C, int Tc, const double *pfac, const double *sqs, const double *kinv,
                                           const double *jcon, const double *ijs, uint64_t seed, int64_t sid,
-                                          const double *dblk, const double *ublk, int m_start) {
+                                          const double *dblk, const double *ublk, int m_start, bool have_z) {
     const int CT = C * Tc, CTm = CT - Tc, RL = CT + 2, ns = s1 - s0;
     if (ns <= 0) return;
     if (dev_stream) {
-        const int npair = (CTm + 1) >> 1;
-        for (int q = pt; q < ns * npair; q += nprod) {
-            const int ds = q / npair, i = q - ds * npair;
-            double z0, z1;
-            dg_normal_pair(seed, sid, (uint32_t)(s0 + ds), (uint32_t)i, z0, z1);
-            zbuf[ds * RL + 2 * i] = z0;
-            if (2 * i + 1 < CTm) zbuf[ds * RL + 2 * i + 1] = z1;
-        }
+        if (!have_z) wide_normals(s0, s1, pt, nprod, zbuf, C, Tc, seed, sid);
         for (int ds = pt; ds < ns; ds += nprod)
             dring[((s0 + ds) % RING) * RL + CT] = dg_log(dg_uniform(seed, sid, (uint32_t)(s0 + ds)));
         wide_sync<BLOCK>();
@@ -323,14 +338,12 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
     double *lens = smem + L.len, *gw = smem + L.gw;
     int *rede = reinterpret_cast<int *>(smem + L.rede), *redb = reinterpret_cast<int *>(smem + L.redb);
     int *rel = reinterpret_cast<int *>(smem + L.ints), *ncnt = rel + (Tc + 1), *cum = ncnt + Tc;
-    unsigned long long *fullb = reinterpret_cast<unsigned long long *>(smem + L.bars);
-    int *relcnt = reinterpret_cast<int *>(fullb + DG_WIDE_MAXSTAGES);
+    unsigned long long *mybars = reinterpret_cast<unsigned long long *>(smem + L.bars) + warp * DG_WIDE_SLOTS;
     double2 *ring2 = reinterpret_cast<double2 *>(smem + L.ring);
     const double prior_const = ct.prior_const[chain];
 
     const int32_t *roff = gt.roff + (size_t)g * (T + 1) + t0;
     const int r_first = roff[0];
-    const double *Wg = gt.W + gt.woff[g] + (size_t)C * r_first;
 
     // ---- per-chain constants ----
     for (int i = tid; i <= Tc; i += nthreads) rel[i] = roff[i] - r_first;
@@ -381,65 +394,48 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
     for (int i = tid; i < NCW * J; i += nthreads) { redm[i] = 1.0; rede[i] = 0; }
     if (tid < NCW) redb[tid] = 0;
     __syncthreads();                                      // rel / ncnt visible
-    if (tid == 0) {
-        int a = 0;
-        for (int t = 0; t < Tc; ++t) { cum[t] = a; a += (((rel[t + 1] - rel[t]) >> 1) + 15) >> 4; }
-        cum[Tc] = a;
-    }
+    const int32_t *toffg = gt.toff + (size_t)g * (T + 1) + t0;
+    for (int i = tid; i <= Tc; i += nthreads) cum[i] = toffg[i] - toffg[0];      // first tile (task) of every time point
     __syncthreads();
+    // ---- this warp's share of W: a contiguous run of tasks, streamed through its OWN ring of TMA slots ----
     const int NT = cum[Tc];                               // tasks per round
-    const int NS = (NT + NCW - 1) / NCW;                  // stages per round
-    const int stage_w2 = NCW * C * 16;                    // double2 per stage
-    int D = ring_bytes / (stage_w2 * 16);
-    if (D > DG_WIDE_MAXSTAGES) D = DG_WIDE_MAXSTAGES;
-    if (D > NS) D = NS;
-    const bool resident = NS <= D;                        // the whole W sits in the ring: loaded once
-    if (tid == 0) {
-        for (int s = 0; s < D; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dg_smem_u32(fullb + s)));
-            relcnt[s] = 0;
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // copies of stage number q (round-periodic) into its ring slot, by the 32 lanes of one warp
+    const int per = (NT + NCW - 1) / NCW;
+    const int ta = is_aux ? 0 : min(warp * per, NT), tb = is_aux ? 0 : min(ta + per, NT);
+    const int ntw = tb - ta;                              // tasks of this warp per round
+    const int task_w2 = C * 16;                           // double2 per task (= tile): [isoform][16 words]
+    const int warp_ring_w2 = ((ring_bytes / NCW) / 16) & ~7;
+    double2 *myring = ring2 + (size_t)warp * warp_ring_w2;
+    const int cap = warp_ring_w2 / task_w2;               // tasks the ring holds
+    const bool resident = ntw <= cap;                     // all of them: loaded once, one barrier, one copy
+    // streaming: chunks of G consecutive tasks (one bulk copy each: the tiles of a gene are contiguous), SL slots
+    const int G = resident ? max(ntw, 1) : max(1, min(4, cap / 4));
+    const int SL = resident ? 1 : min(cap / G, DG_WIDE_SLOTS);
+    const int NC = (ntw + G - 1) / G;                     // chunks per round
+    const double2 *mysrc = reinterpret_cast<const double2 *>(gt.Wt + gt.wtoff[g]) + (size_t)(toffg[0] + ta) * task_w2;
     unsigned long long tma_bytes = 0;
-    auto issue_stage = [&](int q) {
-        const int s = q % NS, rs = q % D;
-        const int task0 = s * NCW, task1 = min(NT, task0 + NCW);
-        int tfirst = 0;
-        while (cum[tfirst + 1] <= task0) ++tfirst;
-        uint32_t words = 0;
-        for (int a = task0, tt = tfirst; a < task1; ++tt) {
-            const int b = min(task1, cum[tt + 1]);
-            const int np = (rel[tt + 1] - rel[tt]) >> 1;
-            const int w0 = (a - cum[tt]) * 16, w1 = min((b - cum[tt]) * 16, np);
-            if (w1 > w0) words += (uint32_t)(w1 - w0);
-            a = b;
-        }
-        const uint32_t bar = dg_smem_u32(fullb + rs);
+    // chunk `c` of this warp's run into ring slot `slot`: ONE bulk copy, issued by lane 0
+    auto issue_chunk = [&](int c, int slot) {
         if (lane == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(words * 16u * (uint32_t)C) : "memory");
-            tma_bytes += (unsigned long long)words * 16u * (unsigned)C;
-        }
-        __syncwarp();
-        for (int a = task0, tt = tfirst; a < task1; ++tt) {
-            const int b = min(task1, cum[tt + 1]);
-            const int np = (rel[tt + 1] - rel[tt]) >> 1;
-            const int w0 = (a - cum[tt]) * 16, w1 = min((b - cum[tt]) * 16, np);
-            if (w1 > w0) {
-                for (int k = lane; k < C; k += 32) {
-                    const double2 *src = reinterpret_cast<const double2 *>(Wg + (size_t)C * rel[tt]) + (size_t)k * np + w0;
-                    double2 *dst = ring2 + (size_t)rs * stage_w2 + (k * NCW + (a - task0)) * 16;
-                    asm volatile(
-                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                        ::"r"(dg_smem_u32(dst)), "l"(src), "r"((uint32_t)(w1 - w0) * 16u), "r"(bar) : "memory");
-                }
-            }
-            a = b;
+            const int first = c * G, n = min(G, ntw - first);
+            const uint32_t bytes = (uint32_t)(n * task_w2) * 16u;
+            const uint32_t bar = dg_smem_u32(mybars + slot);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(dg_smem_u32(myring + (size_t)slot * G * task_w2)), "l"(mysrc + (size_t)first * task_w2), "r"(bytes), "r"(bar)
+                : "memory");
+            tma_bytes += bytes;
         }
     };
+    if (!is_aux && ntw > 0) {
+        if (lane == 0) {
+            for (int s2 = 0; s2 < SL; ++s2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dg_smem_u32(mybars + s2)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        for (int i = 0; i < SL; ++i) issue_chunk(i % NC, i);
+    }
+    int qc = 0;                                           // chunks consumed so far by this warp (slot = qc % SL)
 
     const int m_start = m;
     const int m_end = (m_start + n_steps < M) ? (m_start + n_steps) : M;
@@ -447,22 +443,18 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
     long long page_cur = -1;                              // aux lane 0
     const double *dblk = dev_stream ? nullptr : sa.delta + sa.delta_off[slot_id];
     const double *ublk = dev_stream ? nullptr : sa.u + sa.u_off[slot_id];
-    if (is_aux) {
-        for (int q = 0; q < D; ++q) issue_stage(q);       // prologue: the first D stages
-    }
     int produced = min(m + RING, m_end);                  // ring holds steps [.., produced)
     wide_produce<true>(dev_stream, m, produced, tid, nthreads, zbuf, dring, RING, C, Tc, pfac, sqs, kinv, jcon, ijs,
-                       sa.seed, sid, dblk, ublk, m_start);
+                       sa.seed, sid, dblk, ublk, m_start, false);
 
-    int qs = 0;                                           // stages consumed so far (uniform over the block)
     unsigned long long rounds = 0;
     bool init = (m == 0);                                 // evaluate the start value first (model_GP.py:275-292)
     int next_check = m > initial ? m : initial;
     next_check += (gap - next_check % gap) % gap;
 
 #ifdef DG_PROFILE
-    long long wprof[10];
-    for (int i = 0; i < 10; ++i) wprof[i] = 0;
+    long long wprof[16];
+    for (int i = 0; i < 16; ++i) wprof[i] = 0;
     long long wt0 = clock64();
 #endif
     while (m < m_end || init) {
@@ -517,51 +509,76 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
         // ================= likelihood (consumer warps) || stream + trace pages (aux warp) =================
         bool redo = false;
         do {
+            // the stream rows of the next rounds (ring holds [m, produced) -> up to m + 2J): the normals are made by
+            // the consumer warps (one pair per thread) before their likelihood tasks, the rest by the aux warp
+            const int target = min(m + RING, m_end);
+            const bool top_up = !redo && !init && produced < target;
             if (!is_aux) {
+#ifdef DG_PROFILE
+                long long nt0 = clock64();
+#endif
+                if (top_up) {
+                    if (dev_stream) wide_normals(produced, target, tid, NCW * 32, zbuf, C, Tc, sa.seed, sid);
+                    __threadfence_block();
+                    dg_bar_arrive(1, nthreads);                              // the aux warp waits for them
+                }
+#ifdef DG_PROFILE
+                if (lane == 0 && warp == 0) wprof[12] += clock64() - nt0;
+#endif
                 double mm[RJ], ls[RJ];
                 int ee[RJ];
                 unsigned bad = 0u;
 #pragma unroll
                 for (int n = 0; n < RJ; ++n) { mm[n] = 1.0; ee[n] = 0; ls[n] = 0.0; }
                 int tt = 0, it = 0;
-                int rslot = D > 0 ? qs % D : 0;                                  // ring slot / barrier parity of stage qs
-                uint32_t rphase = D > 0 ? (uint32_t)((qs / D) & 1) : 0u;
-                for (int s = 0; s < NS; ++s) {
-                    mbar_wait(dg_smem_u32(fullb + rslot), resident ? 0u : rphase);
-                    const int task = s * NCW + warp;
-                    if (task < NT) {
+                for (int c = 0; c < NC; ++c) {
+                    const int slot = resident ? 0 : qc % SL;
+#ifdef DG_PROFILE
+                    long long lt0 = clock64();
+#endif
+                    mbar_wait(dg_smem_u32(mybars + slot), resident ? 0u : (uint32_t)((qc / SL) & 1));
+#ifdef DG_PROFILE
+                    long long lt1 = clock64();
+                    if (lane == 0 && warp == 0) wprof[8] += lt1 - lt0;
+#endif
+                    const int first = c * G, n = min(G, ntw - first);
+                    for (int i = 0; i < n; ++i) {
+                        const int task = ta + first + i;
                         while (task >= cum[tt + 1]) ++tt;
                         const int np = (rel[tt + 1] - rel[tt]) >> 1;
                         const int w0 = (task - cum[tt]) * 16;
                         const int nw = min(16, np - w0);
                         const int padw = ((ncnt[tt] & 1) && (w0 + nw == np)) ? nw - 1 : -1;
-                        const double2 *wt = ring2 + (size_t)rslot * stage_w2 + warp * 16;
-                        if (redo) wide_task<KC, RJ, true>(wt, NCW * 16, C, ff + tt * C * J, lane, nw, padw, mm, ee, bad, ls);
-                        else wide_task<KC, RJ, false>(wt, NCW * 16, C, ff + tt * C * J, lane, nw, padw, mm, ee, bad, ls);
-                        if (!redo && (++it & 127) == 0) {                        // keep the running products in range
+                        const double2 *wt = myring + (size_t)(slot * G + i) * task_w2;
+                        if (redo) wide_task<KC, RJ, true>(wt, 16, C, ff + tt * C * J, lane, nw, padw, mm, ee, bad, ls);
+                        else wide_task<KC, RJ, false>(wt, 16, C, ff + tt * C * J, lane, nw, padw, mm, ee, bad, ls);
+                        if (!redo && (++it & 127) == 0) {                    // keep the running products in range
 #pragma unroll
-                            for (int n = 0; n < RJ; ++n) {
-                                const int gq = __double2hiint(mm[n]);
-                                ee[n] += (gq >> 20) - 1023;
-                                mm[n] = dg_mant(mm[n], gq);
+                            for (int n2 = 0; n2 < RJ; ++n2) {
+                                const int gq = __double2hiint(mm[n2]);
+                                ee[n2] += (gq >> 20) - 1023;
+                                mm[n2] = dg_mant(mm[n2], gq);
                             }
                         }
                     }
+#ifdef DG_PROFILE
+                    long long lt2 = clock64();
+                    if (lane == 0 && warp == 0) wprof[9] += lt2 - lt1;
+#endif
                     if (!resident) {
-                        // release the slot; the warp that arrives last re-arms it with stage qs + D
+                        // the slot is free: refill it with the chunk SL ahead (the sequence repeats every round, so the
+                        // first chunks of the next round are on their way while this round decides)
                         __syncwarp();
-                        int old = 0;
-                        if (lane == 0)
-                            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(dg_smem_u32(relcnt + rslot)) : "memory");
-                        old = __shfl_sync(FULL, old, 0);
-                        if (old == NCW - 1) {
-                            if (lane == 0) relcnt[rslot] = 0;
-                            issue_stage(qs + D);
-                        }
+                        issue_chunk((c + SL) % NC, slot);
+                        ++qc;
+#ifdef DG_PROFILE
+                        if (lane == 0 && warp == 0) wprof[13] += clock64() - lt2;
+#endif
                     }
-                    ++qs;
-                    if (++rslot == D) { rslot = 0; rphase ^= 1u; }
                 }
+#ifdef DG_PROFILE
+                long long ft0 = clock64();
+#endif
                 if (redo) {
                     wide_flush<RJ, false>(ls, ee, lane, redm, rede, warp);
                 } else {
@@ -575,8 +592,10 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
                     const unsigned anybad = __ballot_sync(FULL, bad != 0u);
                     if (lane == 0) redb[warp] = anybad ? 1 : 0;
                 }
+#ifdef DG_PROFILE
+                if (lane == 0 && warp == 0) wprof[14] += clock64() - ft0;
+#endif
             } else {
-                qs += NS;
 #ifdef DG_PROFILE
                 const long long at0 = clock64();
 #endif
@@ -594,11 +613,11 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
                         bc[8] = (double)nd_ok;
                     }
                     __syncwarp();
-                    // stream rows of the next rounds: the ring holds steps [m, produced) -> up to m + 2J
-                    const int target = min(m + RING, m_end);
-                    if (!init && produced < target)
+                    if (top_up) {
+                        dg_bar(1, nthreads);                                 // normals in zbuf
                         wide_produce<false>(dev_stream, produced, target, lane, 32, zbuf, dring, RING, C, Tc, pfac, sqs, kinv,
-                                            jcon, ijs, sa.seed, sid, dblk, ublk, m_start);
+                                            jcon, ijs, sa.seed, sid, dblk, ublk, m_start, true);
+                    }
                 }
 #ifdef DG_PROFILE
                 if (lane == 0) wprof[7] += clock64() - at0;
@@ -714,15 +733,18 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
     if (lane == 0 && (warp == 0 || is_aux) && sa.prof) {
         unsigned long long *o = reinterpret_cast<unsigned long long *>(const_cast<double *>(sa.prof));
         for (int i = 0; i < 10; ++i) if (wprof[i]) atomicAdd(o + i, (unsigned long long)wprof[i]);
+        for (int i = 12; i < 16; ++i) if (wprof[i]) atomicAdd(o + i, (unsigned long long)wprof[i]);
         if (warp == 0) { atomicAdd(o + 10, (unsigned long long)(m - m_start)); atomicAdd(o + 11, rounds); }
     }
 #endif
 
     // ---- drain the ring (copies in flight into shared memory), save state ----
-    if (!resident) {
-        for (int q = qs; q < qs + D; ++q) mbar_wait(dg_smem_u32(fullb + q % D), (uint32_t)((q / D) & 1));
-    } else if (D > 0) {
-        for (int q = 0; q < D; ++q) mbar_wait(dg_smem_u32(fullb + q), 0u);
+    if (!is_aux && ntw > 0) {
+        if (resident) mbar_wait(dg_smem_u32(mybars), 0u);
+        else for (int q = qc; q < qc + SL; ++q) mbar_wait(dg_smem_u32(mybars + q % SL), (uint32_t)((q / SL) & 1));
+        __syncwarp();
+        if (lane == 0)
+            for (int s2 = 0; s2 < SL; ++s2) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(dg_smem_u32(mybars + s2)) : "memory");
     }
     __syncthreads();
     {
@@ -745,8 +767,6 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
             atomicAdd(ct.ctr + 3, (unsigned long long)(m - m_start));
             atomicAdd(ct.ctr + 4, rounds * (unsigned long long)J * (unsigned long long)(rel[Tc]) * (unsigned long long)C);
         }
-        for (int s = 0; s < D; ++s)
-            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(dg_smem_u32(fullb + s)) : "memory");
     }
     __syncthreads();
 }
