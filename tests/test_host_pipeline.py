@@ -43,6 +43,46 @@ def test_bam_reader():
         b.fetch("nope", 0, 10)
 
 
+def test_indexed_bam_fetch_equals_full_decode(tmp_path):
+    """IndexedBam (BAI bins + linear index + BGZF virtual offsets) returns exactly the records of the in-memory
+    decode for every gene region and for open-ended regions, and the idxstats totals from the index's
+    pseudo-bins; load_samfile picks it whenever a .bai is present; unsorted files are refused."""
+    import gzip
+    import shutil
+    import struct
+    from diceseq_b200 import bam
+    genes = loadgene(os.path.join(DATA, "yeast_RNA_splicing.gtf"))
+    for t in (1, 4):
+        path = os.path.join(DATA, "reads_t%d.sorted.bam" % t)
+        full, idx = bam.BamFile(path), bam.IndexedBam(path, path + ".bai")
+        assert isinstance(load_samfile(path), bam.IndexedBam)
+        assert full.idxstats() == idx.idxstats() and full.mapped_total() == idx.mapped_total()
+        for g in genes:
+            for a, b in ((g.start, g.stop), (g.start - 500, g.start + 10), (g.stop - 3, g.stop + 2000), (0, 10 ** 7)):
+                ra, rb = full.fetch(g.chrom, a, b), idx.fetch(g.chrom, a, b)
+                assert [(r.qname, r.pos, r.flag, r.cigar) for r in ra] == [(r.qname, r.pos, r.flag, r.cigar) for r in rb]
+    plain = str(tmp_path / "noindex.bam")
+    shutil.copy(os.path.join(DATA, "reads_t1.sorted.bam"), plain)
+    assert isinstance(load_samfile(plain), bam.BamFile)
+    # swap the first two placed records of the uncompressed stream -> not coordinate sorted any more
+    data = bytearray(gzip.open(plain, "rb").read())
+    off = 12 + struct.unpack_from("<i", data, 4)[0]
+    for _ in range(struct.unpack_from("<i", data, off - 4)[0]):
+        off += 8 + struct.unpack_from("<i", data, off)[0]
+    n1 = struct.unpack_from("<i", data, off)[0]
+    n2 = struct.unpack_from("<i", data, off + 4 + n1)[0]
+    last = off
+    while last + 4 + struct.unpack_from("<i", data, last)[0] < len(data):
+        last += 4 + struct.unpack_from("<i", data, last)[0]
+    tail = bytes(data[last:])
+    shuffled = bytes(data[:off]) + tail + bytes(data[off:last])
+    bad = str(tmp_path / "unsorted.bam")
+    with gzip.open(bad, "wb") as f:
+        f.write(shuffled)
+    with pytest.raises(ValueError, match="not sorted"):
+        bam.BamFile(bad)
+
+
 def test_read_model_matches_reference_bit_for_bit():
     z = np.load(os.path.join(ROOT, "tests", "golden", "host_matrices.npz"))
     genes = loadgene(os.path.join(DATA, "yeast_RNA_splicing.gtf"))
