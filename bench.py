@@ -62,17 +62,18 @@ MCMC = dict(M=20000, initial=1000, gap=100)          # diceseq --mcmc default (d
 # ----------------------------------------------------------------------------------------
 def _gen_gene(args):
     from diceseq_b200 import synth
+    from diceseq_b200.packer import pack_gene
     cfg, g = args
-    return synth.gene_W(cfg, g)
+    return pack_gene(*synth.gene_W(cfg, g))               # generated AND packed in the worker
 
 
 def make_batch(cfg, gene_ids, pinned):
     from multiprocessing import get_context
-    from diceseq_b200.packer import pack_genes
+    from diceseq_b200.packer import pack_packed
     nproc = max(2, min(32, os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
     with get_context("fork").Pool(nproc) as pool:
-        genes = pool.map(_gen_gene, [(cfg, int(g)) for g in gene_ids], chunksize=32)
-    return pack_genes(genes, pinned=pinned)
+        items = pool.map(_gen_gene, [(cfg, int(g)) for g in gene_ids], chunksize=32)
+    return pack_packed(items, pinned=pinned)
 
 
 # ----------------------------------------------------------------------------------------

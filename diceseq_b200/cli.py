@@ -67,29 +67,34 @@ def build_parser():
 
 
 def _inputs_worker(args):
-    gene, sam_list, FLmean, FLstd, bias_mode, ref_file, bias_file = args
-    return gene_inputs(gene, sam_list, FLmean, FLstd, bias_mode, ref_file, bias_file)
+    """Matrices of one gene; multi-isoform genes come back cleaned (model_GP.py:250-264) and packed in the device
+    layout (packer.pack_gene), so the process that feeds the GPU only concatenates."""
+    gene, sam_list, FLmean, FLstd, bias_mode, ref_file, bias_file, keep_raw = args
+    R_all, len_all, prob_all, count = gene_inputs(gene, sam_list, FLmean, FLstd, bias_mode, ref_file, bias_file)
+    if gene.tranNum < 2:
+        return None, count
+    if keep_raw:                                                     # theta2-sampling mode works on the raw lists
+        return (R_all, len_all, prob_all), count
+    from .packer import clean_inputs, pack_gene
+    clean_inputs(R_all, len_all, prob_all)
+    return pack_gene([R * P for R, P in zip(R_all, prob_all)], len_all), count
 
 
 def sample_genes(idx, gene_inputs_list, device, batch, sample_num, run_kw, progress=None):
     """Stage 2 on ONE GPU: the multi-isoform genes `idx` (annotation indices, used as the global gene ids of
-    the random streams) in batches of `batch` through BatchSampler (pre-runs, jump variance, joint chains,
+    the random streams; `gene_inputs_list[k]` = the packed matrices of idx[k], packer.pack_gene) in batches of
+    `batch` through BatchSampler (pre-runs, jump variance, joint chains,
     summaries on the device).  Returns ({idx: GeneResult}, {idx: Y samples (n, C, T)}).  Runs in the CLI
     process, or in one worker process per GPU with --gpus."""
     from .batch import BatchSampler, PipelinedSampler
-    from .packer import clean_inputs, pack_genes
+    from .packer import pack_packed
     T = len(run_kw["X"])
     where = {i: k for k, i in enumerate(idx)}
     chunks = [idx[b0:b0 + batch] for b0 in range(0, len(idx), batch)]
 
     def batches():
         for ch in chunks:
-            packed_in = []
-            for i in ch:
-                R_all, len_all, prob_all, _count = gene_inputs_list[where[i]]
-                clean_inputs(R_all, len_all, prob_all)               # model_GP.py:250-264
-                packed_in.append(([R * P for R, P in zip(R_all, prob_all)], len_all))
-            yield pack_genes(packed_in, pinned=len(chunks) > 1), dict(run_kw, gene_ids=np.array(ch))
+            yield pack_packed([gene_inputs_list[where[i]] for i in ch], pinned=len(chunks) > 1), dict(run_kw, gene_ids=np.array(ch))
 
     # several batches: the copy of batch k+1 overlaps the sampling of batch k (two contexts)
     pipe = PipelinedSampler(device) if len(chunks) > 1 else None
@@ -194,7 +199,7 @@ def main(argv=None):
         len(genes), options.device, options.nproc))
 
     # ---- stage 1: host matrices -------------------------------------------------------------
-    jobs = [(g, sam_list, FLmean, FLstd, bias_mode, ref_file, bias_file) for g in genes]
+    jobs = [(g, sam_list, FLmean, FLstd, bias_mode, ref_file, bias_file, theta2 is None) for g in genes]
     if options.nproc <= 1 or len(genes) < 4:
         inputs = [_inputs_worker(j) for j in jobs]
     else:
@@ -217,7 +222,7 @@ def main(argv=None):
             np.random.seed(options.seed)
         dropped = []
         for n_done, i in enumerate(multi):
-            R_all, len_all, prob_all, _count = inputs[i]
+            R_all, len_all, prob_all = inputs[i][0]
             try:
                 r = sample_gene_theta2(R_all, len_all, prob_all, X, theta1, Mmax, Mmin, Mgap, sample_num,
                                        device=options.device)
@@ -252,7 +257,7 @@ def main(argv=None):
         def progress(done):
             sys.stdout.write("\r[DICEseq] %d / %d genes sampled in %.1f sec." % (done, len(multi), time.time() - start_time))
             sys.stdout.flush()
-        res_d, samp_d = sample_genes(multi, [inputs[i] for i in multi], devices[0], options.batch, sample_num, run_kw, progress)
+        res_d, samp_d = sample_genes(multi, [inputs[i][0] for i in multi], devices[0], options.batch, sample_num, run_kw, progress)
         results.update(res_d)
         samples.update(samp_d)
     elif multi:
@@ -260,11 +265,11 @@ def main(argv=None):
         # isoforms x reads, no communication but the final gather of the per-gene results
         import multiprocessing
         from .partition import gene_cost, lpt_partition
-        cost = gene_cost([genes[i].tranNum for i in multi], [sum(r.shape[0] for r in inputs[i][0]) for i in multi])
+        cost = gene_cost([genes[i].tranNum for i in multi], [int(inputs[i][0][1].sum()) for i in multi])
         bins = lpt_partition(cost, n_gpus)
         ctx = multiprocessing.get_context("spawn")
         with ctx.Pool(n_gpus) as pool:
-            jobs2 = [pool.apply_async(sample_genes, ([multi[k] for k in b], [inputs[multi[k]] for k in b],
+            jobs2 = [pool.apply_async(sample_genes, ([multi[k] for k in b], [inputs[multi[k]][0] for k in b],
                                                      devices[r], options.batch, sample_num, run_kw))
                      for r, b in enumerate(bins)]
             for r, j in enumerate(jobs2):
@@ -290,7 +295,7 @@ def main(argv=None):
             fid2 = gzip.open(options.out_file + ".sample.gz", "wt")
             fid2.write("# MCMC samples for latent Y\n# @gene|transcripts|theta2\n# y_c1t1,y_c2t1;y_c1t2,y_c2t2;...\n")
         for i, g in enumerate(genes):
-            count = inputs[i][3]
+            count = inputs[i][1]
             if g.tranNum > 1:
                 if i not in results:
                     continue                                         # dropped (theta2-sampling mode, shape limits)

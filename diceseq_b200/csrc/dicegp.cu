@@ -642,7 +642,7 @@ size_t fixed_smem_bytes(int C, int Tc, int threads, bool streamed, int cs = 1) {
     const int nodes = streamed ? dg_nodes_streamed(C <= 8 ? C : 0) : DG_NODES_RESIDENT;
     return (size_t)dg_layout(C, Tc, (threads + 31) / 32, nodes, cs).total * sizeof(double);
 }
-inline int tier_cluster(int tier) { return (tier < 5 || tier == kWideTier) ? 1 : (2 << (tier - 5)); }
+inline int tier_cluster(int tier) { return (tier < 5 || tier >= kWideTier) ? 1 : (2 << (tier - 5)); }
 
 int64_t chain_reads(const dicegp_ctx *c, int chain) {
     const dicegp_chain_desc &d = c->hdesc[chain];
@@ -1351,11 +1351,11 @@ int dicegp_upload_genes(dicegp_ctx *c, int32_t G, int32_t T, const int32_t *n_is
     c->wt_total = wt_total;
     DG_CUDA(c, cudaMemcpyAsync(c->dwoff.p, c->hwoff.data(), G * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     DG_CUDA(c, cudaMemcpyAsync(c->dlenoff.p, c->hlenoff.data(), G * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-    // W goes up in 16 MB pieces, each submitted when the previous one has landed: another context
+    // W goes up in 64 MB pieces, each submitted when the previous one has landed: another context
     // sampling on this GPU at the same time (PipelinedSampler) issues many small host->device copies,
     // which would otherwise queue behind one multi-GB transfer on the copy engine
-    for (int64_t o = 0; o < w; o += (2 << 20)) {
-        const int64_t cnt = std::min<int64_t>(w - o, 2 << 20);
+    for (int64_t o = 0; o < w; o += (8 << 20)) {          // 64 MB pieces (~1.3 ms each): ~50 host syncs per 3 GB batch
+        const int64_t cnt = std::min<int64_t>(w - o, 8 << 20);
         DG_CUDA(c, cudaMemcpyAsync(c->dW.p + o, W + o, cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         DG_CUDA(c, cudaStreamSynchronize(c->stream));
     }

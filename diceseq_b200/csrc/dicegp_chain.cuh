@@ -342,6 +342,30 @@ __device__ __noinline__ void dg_np_const_stats(double v, int n, double &mean, do
 
 __host__ __device__ inline int dg_geweke_state_len(int CTm) { return 4 + 5 * CTm; }
 
+// Running sums of d = x - K and d^2 over rows first + i (i = warp, warp + nwarps, ... < n) of one column, added
+// (or, SUB, removed) in row order.  Eight rows are loaded at a time: their page-table and value loads are
+// independent, so a lone warp (the warp-per-chain kernels) pays the L2 latency once per eight rows, not twice
+// per row; the arithmetic and its order are unchanged.
+template <bool SUB>
+__device__ __forceinline__ void gw_accum(const TraceView &tv, int first, int n, int warp, int nwarps, int col, double K,
+                                         double &s, double &q) {
+    int i = warp;
+    for (; i + 7 * nwarps < n; i += 8 * nwarps) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(tv.row(first + i + u * nwarps) + col);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double d = v[u] - K;
+            if (!SUB) { s += d; q = fma(d, d, q); } else { s -= d; q = fma(-d, d, q); }
+        }
+    }
+    for (; i < n; i += nwarps) {
+        const double d = __ldcg(tv.row(first + i) + col) - K;
+        if (!SUB) { s += d; q = fma(d, d, q); } else { s -= d; q = fma(-d, d, q); }
+    }
+}
+
 // Runs on the `nwarps` warps (index `warp`) that synchronise on named barrier `bar_id`.
 __device__ __noinline__ int geweke_converged(double *gw, double *gst, int CTm, int nwarps, int warp, int lane,
                                              TraceView tv, int m, int bar_id = 0) {
@@ -367,13 +391,7 @@ __device__ __noinline__ int geweke_converged(double *gw, double *gst, int CTm, i
         if (act) K = haveK ? Kc[col] : __ldcg(tv.row(iB) + col);
         // ---- window A: rows [nA0, nA) enter ----
         double s = 0.0, q = 0.0;
-        if (act) {
-            for (int i = warp; i < addA; i += nwarps) {
-                const double d = __ldcg(tv.row(nA0 + i) + col) - K;
-                s += d;
-                q = fma(d, d, q);
-            }
-        }
+        if (act) gw_accum<false>(tv, nA0, addA, warp, nwarps, col, K, s, q);
         if (lane < GC) { g0[warp * GC + lane] = s; g1[warp * GC + lane] = q; }
         dg_bar(bar_id, nbar);
         double sa = 0.0, qa = 0.0;
@@ -385,16 +403,8 @@ __device__ __noinline__ int geweke_converged(double *gw, double *gst, int CTm, i
         // ---- window B: rows [mB0, m) enter, rows [iB0, iB) leave ----
         s = 0.0; q = 0.0;
         if (act) {
-            for (int i = warp; i < addB; i += nwarps) {
-                const double d = __ldcg(tv.row(mB0 + i) + col) - K;
-                s += d;
-                q = fma(d, d, q);
-            }
-            for (int i = warp; i < subB; i += nwarps) {
-                const double d = __ldcg(tv.row(iB0 + i) + col) - K;
-                s -= d;
-                q = fma(-d, d, q);
-            }
+            gw_accum<false>(tv, mB0, addB, warp, nwarps, col, K, s, q);
+            gw_accum<true>(tv, iB0, subB, warp, nwarps, col, K, s, q);
         }
         if (lane < GC) { g0[warp * GC + lane] = s; g1[warp * GC + lane] = q; }
         dg_bar(bar_id, nbar);

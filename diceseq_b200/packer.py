@@ -60,39 +60,54 @@ class PackedGenes:
                            self.n_reads.reshape(self.G, self.T)[idx].ravel(), W, L)
 
 
+def pack_gene(W_list, len_list):
+    """One gene in the device layout: (flat W, reads per time point, flat len).  Cheap to ship between
+    processes: the matrix workers (bench.py, the CLI's -p pool) pack their own genes so that the process that
+    feeds the GPU only concatenates (`pack_packed`)."""
+    T = len(W_list)
+    if len(len_list) != T:
+        raise ValueError("every gene must have the same number of time points")
+    C = len(len_list[0])
+    n = np.empty(T, dtype=np.int32)
+    for t in range(T):
+        if W_list[t].ndim != 2 or W_list[t].shape[1] != C:
+            raise ValueError("W[t] must be (N_t, C)")
+        n[t] = W_list[t].shape[0]
+    pad = n.astype(np.int64) + (n & 1)
+    flat = np.zeros(int(C * pad.sum()))
+    o = 0
+    for t in range(T):
+        blk = flat[o:o + C * int(pad[t])].reshape(C, int(pad[t]))
+        blk[:, :n[t]] = W_list[t].T
+        o += C * int(pad[t])
+    return flat, n, np.concatenate([np.asarray(l, dtype=np.float64) for l in len_list])
+
+
+def pack_packed(items, pinned=False):
+    """PackedGenes from per-gene `pack_gene` outputs (all with the same number of time points)."""
+    G = len(items)
+    T = len(items[0][1])
+    n_iso = np.array([len(it[2]) // T for it in items], dtype=np.int32)
+    n_reads = np.empty((G, T), dtype=np.int32)
+    for g, it in enumerate(items):
+        if len(it[1]) != T:
+            raise ValueError("every gene must have the same number of time points")
+        n_reads[g] = it[1]
+    W = _alloc(int(sum(it[0].size for it in items)), pinned)
+    L = _alloc(int(sum(it[2].size for it in items)), pinned)
+    wo = lo = 0
+    for flat, _n, lens in items:
+        W[wo:wo + flat.size] = flat
+        wo += flat.size
+        L[lo:lo + lens.size] = lens
+        lo += lens.size
+    return PackedGenes(G, T, n_iso, n_reads.ravel(), W, L)
+
+
 def pack_genes(genes, pinned=False):
     """genes: list of (W_list, len_list) with W_list[t] an (N_t, C) float array and
     len_list[t] a (C,) array; all genes share T = len(W_list)."""
-    G = len(genes)
-    T = len(genes[0][0])
-    n_iso = np.empty(G, dtype=np.int32)
-    n_reads = np.empty((G, T), dtype=np.int32)
-    for g, (W_list, len_list) in enumerate(genes):
-        if len(W_list) != T or len(len_list) != T:
-            raise ValueError("every gene must have the same number of time points")
-        n_iso[g] = len(len_list[0])
-        for t in range(T):
-            if W_list[t].ndim != 2 or W_list[t].shape[1] != n_iso[g]:
-                raise ValueError("W[t] must be (N_t, C)")
-            n_reads[g, t] = W_list[t].shape[0]
-    npad = n_reads.astype(np.int64) + (n_reads & 1)
-    total_w = int((n_iso.astype(np.int64)[:, None] * npad).sum())
-    total_l = int(n_iso.astype(np.int64).sum() * T)
-    W = _alloc(total_w, pinned)
-    L = _alloc(total_l, pinned)
-    wo = lo = 0
-    for g, (W_list, len_list) in enumerate(genes):
-        C = int(n_iso[g])
-        for t in range(T):
-            n, p = int(n_reads[g, t]), int(npad[g, t])
-            blk = W[wo:wo + C * p].reshape(C, p)
-            blk[:, :n] = W_list[t].T
-            if p > n:
-                blk[:, n:] = 0.0
-            wo += C * p
-            L[lo:lo + C] = len_list[t]
-            lo += C
-    return PackedGenes(G, T, n_iso, n_reads.ravel(), W, L)
+    return pack_packed([pack_gene(W_list, len_list) for W_list, len_list in genes], pinned)
 
 
 def _alloc(n, pinned):
