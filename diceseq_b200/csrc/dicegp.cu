@@ -368,13 +368,21 @@ __device__ void dg_radix_select2(const unsigned long long *keys, int n, int rank
     out1 = prefix[1];
 }
 
+// One block per chain, two phases.
+//   1. The rows kept after the burn-in are read ONCE, coalesced (chunks of <= 64 trace columns through a
+//      32-row shared-memory tile): the column means are accumulated in row order and the columns are written
+//      back TRANSPOSED into a scratch (column-major: n contiguous doubles per column, the log-likelihood as one
+//      more column).  A trace row is 2CT+2 doubles, so reading one column straight from the trace touches one
+//      128-byte line per value; the round-1 kernel read 105 GB for 19 GB of trace that way.
+//   2. Per column: the keys come from the scratch (contiguous), exact order statistics by radix select.
+#define DG_SUM_TILE_COLS 64
 __global__ void __launch_bounds__(DG_SUM_THREADS)
 dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, double *__restrict__ mean_out,
                       double *__restrict__ ci_out, const int64_t *__restrict__ out_off, double *__restrict__ lik_out,
-                      unsigned long long *gkeys, size_t gstride) {
+                      double *__restrict__ scratch, const int64_t *__restrict__ scr_off, int keys_in_smem) {
     extern __shared__ __align__(16) unsigned long long dg_keys_smem[];
-    // one column of keys: in shared memory, or (chains that keep more rows than fit) in a global scratch row
-    unsigned long long *dg_keys = gkeys ? gkeys + (size_t)blockIdx.x * gstride : dg_keys_smem;
+    // phase 1 uses the dynamic shared memory as a 32 x 65 tile, phase 2 as one column of keys
+    double (*tile)[DG_SUM_TILE_COLS + 1] = reinterpret_cast<double (*)[DG_SUM_TILE_COLS + 1]>(dg_keys_smem);
     __shared__ unsigned hist[512];
     __shared__ int sh[4];
     __shared__ double red[DG_SUM_THREADS / 32];
@@ -395,35 +403,55 @@ dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, 
         if (tid == 0) lik_out[blockIdx.x] = nan("");
         return;
     }
-    // mean: one thread per column, rows in order
-    for (int col = tid; col < CT; col += blockDim.x) {
+    double *cols = scratch + scr_off[blockIdx.x];                 // (CT + 1) columns of n doubles
+    // ---- phase 1: means (rows in order, like numpy's axis-0 reduction) + transposed copy ----
+    for (int c0 = 0; c0 < CT; c0 += DG_SUM_TILE_COLS) {
+        const int w = min(DG_SUM_TILE_COLS, CT - c0);
+        const bool last = c0 + w == CT;
+        const int wl = w + (last && w < DG_SUM_TILE_COLS ? 1 : 0);   // the log-likelihood column rides along when there is room
         double a = 0.0;
-        int r = 0;
-        for (; r + 4 <= n; r += 4) {
-            const double v0 = __ldcg(tv.row(b + r) + col), v1 = __ldcg(tv.row(b + r + 1) + col);
-            const double v2 = __ldcg(tv.row(b + r + 2) + col), v3 = __ldcg(tv.row(b + r + 3) + col);
-            a += v0; a += v1; a += v2; a += v3;
+        for (int r0 = 0; r0 < n; r0 += 32) {
+            const int nr = min(32, n - r0);
+            for (int idx = tid; idx < nr * wl; idx += DG_SUM_THREADS) {
+                const int r = idx / wl, j = idx - r * wl;
+                tile[r][j] = __ldcg(tv.row(b + r0 + r) + (j < w ? c0 + j : 2 * CT + 1));
+            }
+            __syncthreads();
+            if (tid < w) for (int r = 0; r < nr; ++r) a += tile[r][tid];
+            for (int idx = tid; idx < wl * 32; idx += DG_SUM_THREADS) {
+                const int j = idx >> 5, r = idx & 31;
+                if (r < nr) cols[(size_t)(j < w ? c0 + j : CT) * n + r0 + r] = tile[r][j];
+            }
+            __syncthreads();
         }
-        for (; r < n; ++r) a += __ldcg(tv.row(b + r) + col);
-        mean[col] = a / (double)n;
+        if (tid < w) mean[c0 + tid] = a / (double)n;
+        if (last && wl == w) {                                    // no room in the last chunk: the log-likelihood column alone
+            for (int i = tid; i < n; i += DG_SUM_THREADS) cols[(size_t)CT * n + i] = __ldcg(tv.row(b + i) + 2 * CT + 1);
+        }
     }
-    // interval: per column radix select of ranks k and n-k (k = 0 -> both the minimum side quirk)
+    __syncthreads();
+    // ---- phase 2: per column radix select of ranks k and n-k (k = 0 -> both the minimum side quirk) ----
     const int k = (int)((double)n * (1.0 - 0.95) / 2.0);
     for (int col = 0; col < CT; ++col) {
-        __syncthreads();
-        for (int i = tid; i < n; i += blockDim.x)
-            dg_keys[i] = (unsigned long long)__double_as_longlong(__ldcg(tv.row(b + i) + col));
-        __syncthreads();
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(cols + (size_t)col * n);
+        const unsigned long long *keys = src;                     // long chains select in the scratch itself
+        if (keys_in_smem) {
+            __syncthreads();
+            for (int i = tid; i < n; i += blockDim.x) dg_keys_smem[i] = __ldcg(src + i);
+            __syncthreads();
+            keys = dg_keys_smem;
+        }
         unsigned long long lo, hi;
-        dg_radix_select2(dg_keys, n, k, k > 0 ? n - k : 0, hist, sh, lo, hi);
+        dg_radix_select2(keys, n, k, k > 0 ? n - k : 0, hist, sh, lo, hi);
         if (tid == 0) {
             ci[2 * col] = __longlong_as_double((long long)hi);       // sorted[-k]
             ci[2 * col + 1] = __longlong_as_double((long long)lo);   // sorted[k]
         }
     }
     // harmonic-mean log-likelihood
+    const double *lk = cols + (size_t)CT * n;
     double mn = INFINITY;
-    for (int i = tid; i < n; i += blockDim.x) mn = fmin(mn, __ldcg(tv.row(b + i) + 2 * CT + 1));
+    for (int i = tid; i < n; i += blockDim.x) mn = fmin(mn, __ldcg(lk + i));
     for (int off = 16; off > 0; off >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
     __syncthreads();
     if (lane == 0) red[warp] = mn;
@@ -431,7 +459,7 @@ dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, 
     mn = red[0];
     for (int w = 1; w < DG_SUM_THREADS / 32; ++w) mn = fmin(mn, red[w]);
     double se = 0.0;
-    for (int i = tid; i < n; i += blockDim.x) se += exp(mn - __ldcg(tv.row(b + i) + 2 * CT + 1));
+    for (int i = tid; i < n; i += blockDim.x) se += exp(mn - __ldcg(lk + i));
     for (int off = 16; off > 0; off >>= 1) se += __shfl_xor_sync(0xffffffffu, se, off);
     __syncthreads();
     if (lane == 0) red[warp] = se;
@@ -555,7 +583,8 @@ struct dicegp_ctx {
     DevBuf<double> ddelta, du, dvar;
     DevBuf<int> dqueue;
     DevBuf<double> smean, sci, slik;       // posterior summary scratch
-    DevBuf<unsigned long long> skeys;      // radix-select keys of chains too long for shared memory
+    DevBuf<unsigned long long> skeys;      // posterior summary: the kept trace rows transposed (column-major per chain)
+    DevBuf<int64_t> sscr_off;              // ... first double of every chain's columns
     DevBuf<double> deval;                  // eval_loglik scratch: y | per-block partial sums | lik
     DevBuf<unsigned> deval_done;
     DevBuf<int64_t> soff;
@@ -563,6 +592,7 @@ struct dicegp_ctx {
     DevBuf<unsigned long long> dprof;
     DevBuf<unsigned long long> dctr;        // work counters of the chain kernels (ChainTab::ctr)
     size_t static_smem_wide = 0;
+    int wide_cluster_cap[4] = {0, 0, 0, 0};   // chains the wide-round kernel runs at once on clusters of 1 / 2 / 4 / 8 blocks
     double last_ms = 0.0;
     int64_t last_launches = 0, last_evals = 0, last_steps = 0;
     std::vector<int32_t> hm_next_before;
@@ -604,6 +634,7 @@ ChainTab make_chain_tab(dicegp_ctx *c) {
     t.trace = c->ctrace.p; t.st = c->cst.p; t.m_next = c->cm_next.p; t.cnt = c->ccnt.p;
     t.state = c->cstate.p; t.m_ret = c->cm_ret.p; t.flags = c->cflags.p;
     t.ctr = c->dctr.p;
+    t.l2pin = 0;
     return t;
 }
 
@@ -637,6 +668,10 @@ void launch_classes(const dicegp_ctx *c, LaunchClass out[kTiers]) {
     }
 }
 
+// warps of a block that own a cp.async staging ring: all of them, unless the state warps take no likelihood items
+inline int ring_warps(int threads, int C, int Tc) {
+    return DG_STATE_LIK_WEIGHT > 0 ? threads / 32 : threads / 32 - (C * Tc + 31) / 32;
+}
 // shared memory of a chain besides W / the staging rings; `streamed`: tiers 4-7
 size_t fixed_smem_bytes(int C, int Tc, int threads, bool streamed, int cs = 1) {
     const int nodes = streamed ? dg_nodes_streamed(C <= 8 ? C : 0) : DG_NODES_RESIDENT;
@@ -693,8 +728,8 @@ WidePlan wide_plan(int C, int latency_mode) {
     // one chain's round overlaps the likelihood pass of the other).  DICEGP_WIDE_NCW / _BPS / _RJ override.
     static const int e_ncw = env_int("DICEGP_WIDE_NCW", 0), e_bps = env_int("DICEGP_WIDE_BPS", 0), e_rj = env_int("DICEGP_WIDE_RJ", 0);
     WidePlan p;
-    p.rj = (e_rj == 2 || e_rj == 4) ? e_rj : 4;
-    (void)latency_mode; (void)C;
+    p.rj = 4;
+    (void)latency_mode; (void)C; (void)e_rj;
     p.ncw = 16; p.bps = 1;
     if (e_ncw > 0) p.ncw = std::min(e_ncw, DG_WIDE_THREADS / 32 - 1);
     if (e_bps > 0) p.bps = e_bps;
@@ -723,17 +758,17 @@ bool wide_eligible(const dicegp_ctx *c, int chain, int latency_mode) {
 }
 
 typedef void (*wide_kernel_t)(GeneTab, ChainTab, StreamArgs, const int32_t *, int, int, int, int *);
-wide_kernel_t wide_kernel_for(int kind, int rj) {
-    if (rj == 2) {
+wide_kernel_t wide_kernel_for(int kind, bool cluster) {
+    if (cluster) {
         switch (kind) {
-            case 0: return dicegp_wide_kernel<0, 2>;
-            case 1: return dicegp_wide_kernel<2, 2>;
-            case 2: return dicegp_wide_kernel<3, 2>;
-            case 3: return dicegp_wide_kernel<4, 2>;
-            case 4: return dicegp_wide_kernel<5, 2>;
-            case 5: return dicegp_wide_kernel<6, 2>;
-            case 6: return dicegp_wide_kernel<7, 2>;
-            default: return dicegp_wide_kernel<8, 2>;
+            case 0: return dicegp_wide_kernel<0, 4, true>;
+            case 1: return dicegp_wide_kernel<2, 4, true>;
+            case 2: return dicegp_wide_kernel<3, 4, true>;
+            case 3: return dicegp_wide_kernel<4, 4, true>;
+            case 4: return dicegp_wide_kernel<5, 4, true>;
+            case 5: return dicegp_wide_kernel<6, 4, true>;
+            case 6: return dicegp_wide_kernel<7, 4, true>;
+            default: return dicegp_wide_kernel<8, 4, true>;
         }
     }
     switch (kind) {
@@ -806,6 +841,32 @@ chain_kernel_t chain_kernel_for(int kind, bool w_in_smem, bool cluster) {
     }
 }
 
+// How many chains the wide-round kernel can run at once with a cluster of `cs` blocks per chain (one block per SM;
+// clusters do not span GPCs, so this is less than SMs / cs): asked of the driver once per context.
+int wide_cluster_capacity(dicegp_ctx *c, int cs) {
+    const int slot = cs >= 8 ? 3 : (cs >= 4 ? 2 : (cs >= 2 ? 1 : 0));
+    if (cs <= 1) return c->sm_count;
+    if (c->wide_cluster_cap[slot] == 0) {
+        wide_kernel_t kern = wide_kernel_for(7, true);
+        const int smem = (int)(c->smem_optin - c->static_smem_wide);
+        int n = 0;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(c->sm_count / cs * cs); cfg.blockDim = dim3(DG_WIDE_THREADS - 32); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = c->sm_count / cs * 3 / 4;                      // conservative guess
+        }
+        c->wide_cluster_cap[slot] = n;
+    }
+    return c->wide_cluster_cap[slot];
+}
+
 // The tiled copy of W (wide-round kernel), built once per uploaded batch, when a wide launch first needs it.
 int ensure_tiles(dicegp_ctx *c) {
     if (c->tiles_valid) return DICEGP_OK;
@@ -833,6 +894,15 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     }
     std::vector<int32_t> by_group[kGroups];
     std::vector<int32_t> slot_src[kGroups];
+    // last stragglers (latency_mode 2): fewer chains than SMs, so every chain of the wide-round kernel gets a
+    // thread-block cluster -- the largest of 8 / 4 / 2 blocks that still lets all chains run at once
+    int wide_cs = 1;
+    if (latency_mode == 2 && persistent) {
+        const int n = (int)ids.size();
+        const int e_cs = env_int("DICEGP_WIDE_CS", 0);
+        wide_cs = n <= wide_cluster_capacity(c, 8) ? 8 : (n <= wide_cluster_capacity(c, 4) ? 4 : (n <= wide_cluster_capacity(c, 2) ? 2 : 1));
+        if (e_cs == 1 || e_cs == 2 || e_cs == 4 || e_cs == 8) wide_cs = e_cs;
+    }
     for (size_t i = 0; i < ids.size(); ++i) {
         const dicegp_chain_desc &d = c->hdesc[ids[i]];
         const int C = c->hC[d.gene];
@@ -929,18 +999,35 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                     sak.delta_off = c->ddoff.p + base[k];
                     sak.u_off = c->ddoff.p + flat.size() + base[k];
                 }
+                const int wcs = wide_cs;
                 int grid = n_ids;
                 int *queue = nullptr;
                 if (persistent) {
-                    grid = std::min(n_ids, c->sm_count * wp.bps);
+                    grid = std::min(n_ids, wcs > 1 ? wide_cluster_capacity(c, wcs) : c->sm_count * wp.bps);
                     queue = c->dqueue.p + k;
                 }
-                wide_kernel_t kern = wide_kernel_for(kind, wp.rj);
+                grid *= wcs;
+                wide_kernel_t kern = wide_kernel_for(kind, wcs > 1);
                 DG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(c->smem_optin - c->static_smem_wide)));
-                kern<<<grid, 32 * (wp.ncw + 1), smem, st>>>(gt, ct, sak, c->dids.p + base[k], n_ids, n_steps, (int)ring_bytes, queue);
+                if (wcs > 1) {
+                    int rc = preallocate_trace_pages(c, by_group[k]);      // only the lead block writes the trace
+                    if (rc != DICEGP_OK) return rc;
+                }
+                if (getenv("DICEGP_VERBOSE"))
+                    fprintf(stderr, "[dicegp]   launch wide C-kind %d: %d chains, %d threads, cluster %d, %zu B smem, grid %d\n",
+                            kind == 0 ? 0 : kind + 1, n_ids, 32 * (wp.ncw + 1), wcs, smem, grid);
                 {
-                    cudaError_t e = cudaGetLastError();
+                    cudaLaunchConfig_t cfg;
+                    memset(&cfg, 0, sizeof cfg);
+                    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * (wp.ncw + 1)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeClusterDimension;
+                    attr[0].val.clusterDim.x = wcs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                    cfg.attrs = attr; cfg.numAttrs = wcs > 1 ? 1 : 0;
+                    const int32_t *ids_arg = c->dids.p + base[k];
+                    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, gt, ct, sak, ids_arg, n_ids, n_steps, (int)ring_bytes, queue);
+                    if (e == cudaSuccess) e = cudaGetLastError();
                     if (e != cudaSuccess) return c->cuda_fail(e, "wide chain kernel launch");
                 }
                 ++launches;
@@ -963,21 +1050,29 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             }
             const int cs = tier_cluster(tier);
             if (tier == 4 && !getenv("DICEGP_TIER_THREADS")) {
+                // every warp of a block streams W (the state warps join the likelihood pass after the prior terms),
+                // so every warp owns a staging ring
                 int best_score = -1;
                 for (int kk = 1; kk <= (latency_mode ? 1 : 4); ++kk) {
-                    for (int nwl = 2; nwl <= DG_LB_THREADS / 32 - 2; ++nwl) {
+                    for (int nwl = 1; nwl <= DG_LB_THREADS / 32 - 1; ++nwl) {
                         const int thr = 32 * (maxS + nwl);
                         if (thr * kk > DG_LB_THREADS) continue;
                         size_t need = fixed_smem_bytes(maxC, maxTc, thr, true) + 1024;
-                        if (kind != 0) need += (size_t)nwl * dg::dg_stages(maxC) * dg::dg_stage_slot_bytes(maxC);
+                        if (kind != 0) need += (size_t)ring_warps(thr, maxC, maxTc) * dg::dg_stages(maxC) * dg::dg_stage_slot_bytes(maxC);
                         if (need * kk > 233472 || need - 1024 + 127 > c->smem_optin - c->static_smem) continue;
-                        // at least 8 streaming warps per SM, then as many chains as possible (their serial
-                        // phases overlap), then more warps
-                        const int score = latency_mode ? nwl : std::min(kk * nwl, 8) * 100 + kk * 10 + nwl;
+                        // measured per isoform count on the bench workload (scripts/class_timing.py): ten streaming warps
+                        // per SM first, then three chains per SM rather than two or four (their serial phases overlap; a
+                        // fourth chain only shrinks everybody's share of warps), then more warps per chain
+                        const int score = latency_mode ? nwl
+                                        : std::min(kk * ring_warps(thr, maxC, maxTc), 10) * 100 - 15 * std::abs(kk - 3) + nwl;
                         if (score > best_score) { best_score = score; threads = thr; bps = kk; }
                     }
                 }
                 if (best_score < 0) return c->fail(DICEGP_ERR_LIMIT, "chain has too many latent values for the streaming tier");
+                // development override: DICEGP_PLAN_K<C> = "threads,blocks per SM" for the streamed launch of C isoforms
+                char name[32];
+                snprintf(name, sizeof name, "DICEGP_PLAN_K%d", kind == 0 ? 0 : kind + 1);
+                if (const char *e = getenv(name)) sscanf(e, "%d,%d", &threads, &bps);
             }
             if (tier >= 5) {
                 // cluster tier: as many likelihood warps per block as the staging ring allows
@@ -986,7 +1081,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                     const int thr = 32 * (maxS + nwl);
                     if (thr > DG_LB_THREADS) break;
                     size_t need = fixed_smem_bytes(maxC, maxTc, thr, true, cs) + 1024;
-                    if (kind != 0) need += (size_t)nwl * dg::dg_stages(maxC) * dg::dg_stage_slot_bytes(maxC);
+                    if (kind != 0) need += (size_t)ring_warps(thr, maxC, maxTc) * dg::dg_stages(maxC) * dg::dg_stage_slot_bytes(maxC);
                     if (need > 233472 || need - 1024 + 127 > c->smem_optin - c->static_smem) break;
                     best = thr;
                 }
@@ -1002,10 +1097,9 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                 size_t need = fixed_smem_bytes(c->hC[d.gene], d.Tc, threads, tier >= 4, cs);
                 if (cls[tier].w_in_smem) need += (size_t)chain_wbytes(c, id);
                 else if (kind != 0) {
-                    // per likelihood warp: kStages x C x 32 lanes x 16 bytes of cp.async staging
+                    // per warp: kStages x C x 32 lanes x 16 bytes of cp.async staging
                     const int C = c->hC[d.gene];
-                    const int nwl = threads / 32 - (C * d.Tc + 31) / 32;
-                    need += (size_t)nwl * dg::dg_stages(C) * dg::dg_stage_slot_bytes(C);
+                    need += (size_t)ring_warps(threads, C, d.Tc) * dg::dg_stages(C) * dg::dg_stage_slot_bytes(C);
                 }
                 smem = std::max(smem, need);
             }
@@ -1028,6 +1122,9 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             grid *= cs;
             // the streamed tiers all use the cluster-capable variants (cluster size 1 for tier 4): their code
             // schedule is also the faster one for a single block (measured)
+            if (getenv("DICEGP_VERBOSE"))
+                fprintf(stderr, "[dicegp]   launch tier %d C-kind %d: %d chains, %d threads x %d blocks/SM (cluster %d), %zu B smem, grid %d\n",
+                        tier, kind == 0 ? 0 : kind + 1, n_ids, threads, bps, cs, smem, grid);
             chain_kernel_t kern = chain_kernel_for(kind, cls[tier].w_in_smem, tier >= 4);
             DG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(c->smem_optin - c->static_smem)));
@@ -1040,7 +1137,15 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                 attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
                 cfg.attrs = attr; cfg.numAttrs = 1;
                 const int32_t *ids_arg = c->dids.p + base[k];
-                cudaError_t e = cudaLaunchKernelEx(&cfg, kern, gt, ct, sak, ids_arg, n_ids, n_steps, c->use_tma, queue);
+                ChainTab ctk = ct;
+                if (tier == 4 && kind != 0) {
+                    // development knob: DICEGP_L2_PIN = "p2,p3,...,p8", sixteenths of W kept in L2 per isoform count
+                    int pins[9] = {0};
+                    if (const char *e = getenv("DICEGP_L2_PIN"))
+                        sscanf(e, "%d,%d,%d,%d,%d,%d,%d", &pins[2], &pins[3], &pins[4], &pins[5], &pins[6], &pins[7], &pins[8]);
+                    ctk.l2pin = pins[kind + 1];
+                }
+                cudaError_t e = cudaLaunchKernelEx(&cfg, kern, gt, ctk, sak, ids_arg, n_ids, n_steps, c->use_tma, queue);
                 if (e == cudaSuccess) e = cudaGetLastError();
                 if (e != cudaSuccess) return c->cuda_fail(e, "chain kernel launch");
             }
@@ -1083,11 +1188,11 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             for (int i = 0; i < 8; ++i) { fprintf(stderr, " %s=%.0f", nm[i], h[i] / n); if (i < 7) tot += h[i] / n; }
             fprintf(stderr, " total=%.0f | within lik (warp 0): barrier wait=%.0f task=%.0f normals=%.0f issue=%.0f flush=%.0f\n", tot, h[8] / n, h[9] / n, h[12] / n, h[13] / n, h[14] / n);
         } else {
-            const char *nm[9] = {"S", "window", "B2wait", "decide", "update", "geweke", "-", "-", "-"};
+            const char *nm[9] = {"S", "prior", "B2wait", "decide", "update", "geweke", "lik(warp0)", "-", "-"};
             double n = (double)std::max<unsigned long long>(h[10], 1);
             fprintf(stderr, "[dg_prof] steps=%llu cycles/step:", h[10]);
             double tot = 0;
-            for (int i = 0; i < 6; ++i) { fprintf(stderr, " %s=%.0f", nm[i], h[i] / n); tot += h[i] / n; }
+            for (int i = 0; i < 7; ++i) { fprintf(stderr, " %s=%.0f", nm[i], h[i] / n); tot += h[i] / n; }
             fprintf(stderr, " total=%.0f\n", tot);
         }
     }
@@ -1263,7 +1368,7 @@ int dicegp_destroy(dicegp_ctx *c) {
     c->cprior.release(); c->cpool.release(); c->ctrace.release(); c->cst.release();
     c->dids.release(); c->ddoff.release(); c->ddelta.release(); c->du.release(); c->dvar.release();
     c->dqueue.release(); c->deval.release(); c->deval_done.release(); c->dctr.release(); c->dprof.release();
-    c->smean.release(); c->sci.release(); c->slik.release(); c->skeys.release(); c->soff.release(); c->sids.release();
+    c->smean.release(); c->sci.release(); c->slik.release(); c->skeys.release(); c->sscr_off.release(); c->soff.release(); c->sids.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1627,25 +1732,37 @@ int dicegp_run_device_stream(dicegp_ctx *c, uint64_t seed, const int64_t *stream
     // each while the rest of the GPU idles.  The stream is counter based, so a resumed chain
     // continues bit-identically.  (An optional third pass on clusters of 4 blocks exists for
     // experiments -- DICEGP_STRAGGLER_STEPS=a,b -- but measured slower on the bench workload.)
+    // Further passes when the stragglers are few (a rank of a multi-GPU run, a small batch): with fewer chains than
+    // SMs what is left is bound by the chains that use all M steps, so the survivors of every 4096 more steps are
+    // re-launched on thread-block clusters of 2 / 4 / 8 SMs per chain (wide-round kernel, DSMEM exchange) as soon as
+    // that many SMs per chain are free; once the clusters have their full size the chains run to the end.
+    // DICEGP_STRAGGLER_STEPS=a[,b] fixes the plan instead (a: cap of pass 0; b: cap of a pass 1 before the cluster pass).
     int cap0 = 4096, cap1 = 0;
+    const bool fixed_plan = getenv("DICEGP_STRAGGLER_STEPS") != nullptr;
     if (const char *e = getenv("DICEGP_STRAGGLER_STEPS")) sscanf(e, "%d,%d", &cap0, &cap1);
     if (cap0 <= 0 || max_M <= cap0) return run_chains(c, ids, max_M, sa, nullptr, true, 0);
-    std::vector<std::pair<int, int>> plan;                      // (absolute step cap, shape mode)
-    plan.push_back({cap0, 0});
-    if (cap1 > cap0 && cap1 < max_M) { plan.push_back({cap1, 1}); plan.push_back({max_M, 2}); }
-    else plan.push_back({max_M, 1});
     double ms = 0.0;
     int64_t launches = 0, evals = 0, steps = 0;
     std::vector<int32_t> todo = ids;
     int prev = 0;                                               // steps every chain in `todo` has done
-    for (size_t pass = 0; pass < plan.size() && !todo.empty(); ++pass) {
-        const int cap = plan[pass].first;
-        int rc = run_chains(c, todo, cap - prev, sa, nullptr, true, plan[pass].second);
+    for (int pass = 0; !todo.empty() && prev < max_M; ++pass) {
+        int cap, mode;
+        const int n = (int)todo.size();
+        if (pass == 0) { cap = cap0; mode = 0; }
+        else if (fixed_plan) {
+            if (pass == 1 && cap1 > cap0 && cap1 < max_M) { cap = cap1; mode = 1; }
+            else { cap = max_M; mode = (cap1 > cap0 && cap1 < max_M) ? 2 : 1; }
+        } else if (n > 4 * c->sm_count) { cap = max_M; mode = 1; }       // throughput bound: one chain per SM to the end
+        else {
+            mode = n <= wide_cluster_capacity(c, 2) ? 2 : 1;              // clusters as soon as two SMs per chain are free
+            cap = n <= wide_cluster_capacity(c, 8) ? max_M : std::min(max_M, prev + 4096);
+        }
+        int rc = run_chains(c, todo, cap - prev, sa, nullptr, true, mode);
         if (rc != DICEGP_OK) return rc;
         prev = cap;
         if (getenv("DICEGP_VERBOSE"))
-            fprintf(stderr, "[dicegp] pass %zu (cap %d, mode %d): %.1f ms, %lld steps, %zu chains\n", pass, cap,
-                    plan[pass].second, c->last_ms, (long long)c->last_steps, todo.size());
+            fprintf(stderr, "[dicegp] pass %d (cap %d, mode %d): %.1f ms, %lld steps, %zu chains\n", pass, cap,
+                    mode, c->last_ms, (long long)c->last_steps, todo.size());
         ms += c->last_ms; launches += c->last_launches; evals += c->last_evals; steps += c->last_steps;
         if (cap >= max_M) break;
         std::vector<int32_t> st(c->n_chains);
@@ -1804,12 +1921,18 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
         }
     }
     gstart[kClasses] = (int)order.size();
-    const int n_huge = gstart[5] - gstart[4];
-    if (n_huge > 0 && c->skeys.resize((size_t)n_huge * gmax[4]) != cudaSuccess)
-        return c->fail(DICEGP_ERR_NOMEM, "posterior_summary: device allocation failed (select scratch)");
     std::vector<int32_t> ids_sorted(n);
-    std::vector<int64_t> off_sorted(n);
-    for (int i = 0; i < n; ++i) { ids_sorted[i] = chain_ids[order[i]]; off_sorted[i] = out_off[order[i]]; }
+    std::vector<int64_t> off_sorted(n), scr_sorted(n);
+    int64_t scr_total = 0;                 // transposed copy of the kept rows: (CT + 1) columns of `keep` doubles per chain
+    for (int i = 0; i < n; ++i) {
+        ids_sorted[i] = chain_ids[order[i]]; off_sorted[i] = out_off[order[i]];
+        const dicegp_chain_desc &d = c->hdesc[ids_sorted[i]];
+        const int keep = std::max(0, nr[order[i]] - (mr[order[i]] > 0 ? mr[order[i]] >> 2 : 0));
+        scr_sorted[i] = scr_total;
+        scr_total += (int64_t)keep * ((int64_t)c->hC[d.gene] * d.Tc + 1);
+    }
+    if (c->skeys.resize((size_t)std::max<int64_t>(scr_total, 1)) != cudaSuccess || c->sscr_off.resize(n) != cudaSuccess)
+        return c->fail(DICEGP_ERR_NOMEM, "posterior_summary: device allocation failed (transposed trace scratch)");
     DevBuf<double> &dmean = c->smean, &dci = c->sci, &dlik = c->slik;
     DevBuf<int64_t> &doff = c->soff;
     DevBuf<int32_t> &dids = c->sids;
@@ -1822,6 +1945,7 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
     do {
         if ((e = cudaMemcpyAsync(doff.p, off_sorted.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(dids.p, ids_sorted.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(c->sscr_off.p, scr_sorted.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
         if ((e = cudaFuncSetAttribute(dicegp_summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - 4096))) != cudaSuccess) break;
         // the size classes run side by side (the few long chains keep only some SMs busy, for as long
         // as the thousands of short ones take all together): longest first, one stream each.
@@ -1832,12 +1956,13 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
         for (int k = kClasses - 1; k >= 0 && e == cudaSuccess; --k) {
             const int cnt = gstart[k + 1] - gstart[k];
             if (cnt == 0) continue;
-            const size_t sm = k == 4 ? 0 : (size_t)gmax[k] * sizeof(unsigned long long);
+            const size_t sm = std::max<size_t>(k == 4 ? 0 : (size_t)gmax[k] * sizeof(unsigned long long),
+                                               32 * (DG_SUM_TILE_COLS + 1) * sizeof(double));
             cudaStream_t st = c->class_stream[k];
             if ((e = cudaStreamWaitEvent(st, c->ev_fork, 0)) != cudaSuccess) break;
             dicegp_summary_kernel<<<cnt, DG_SUM_THREADS, sm, st>>>(make_gene_tab(c), make_chain_tab(c), dids.p + gstart[k],
                                                                    dmean.p, dci.p, doff.p + gstart[k], dlik.p + gstart[k],
-                                                                   k == 4 ? c->skeys.p : nullptr, (size_t)gmax[4]);
+                                                                   reinterpret_cast<double *>(c->skeys.p), c->sscr_off.p + gstart[k], k == 4 ? 0 : 1);
             ++c->total_launches;
             if ((e = cudaGetLastError()) != cudaSuccess) break;
             if ((e = cudaEventRecord(c->ev_join[k], st)) != cudaSuccess) break;

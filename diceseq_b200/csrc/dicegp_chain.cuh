@@ -61,6 +61,10 @@ __device__ __forceinline__ double dg_mant(double x, int hi) {
 //               copies exactly the 16-byte words it will consume: no barrier, deep prefetch)
 //   W_DIRECT    plain global loads (isoform counts too large for the staging ring)
 enum { W_RESIDENT = 0, W_STAGED = 1, W_DIRECT = 2 };
+// share of the likelihood items a state warp takes, in sixteenths of a likelihood warp's share
+#ifndef DG_STATE_LIK_WEIGHT
+#define DG_STATE_LIK_WEIGHT 12
+#endif
 // Shape of a likelihood item, per isoform count C:
 //   words   16-byte words (read pairs) a lane handles per item.  The words of a lane are independent
 //           dependency chains in one basic block, which the scheduler interleaves (a likelihood
@@ -90,13 +94,29 @@ __host__ __device__ constexpr int dg_stages(int C) {
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dg_smem_u32(dst_smem)), "l"(src) : "memory");
 }
+// the same copy with an L2 eviction policy (createpolicy): part of every chain's W is kept in L2 with
+// evict_last while the rest streams through with evict_first, so that a working set larger than L2 does
+// not thrash it (a cyclic sweep over more bytes than the cache holds hits nothing under LRU)
+__device__ __forceinline__ void cp_async16_hint(void *dst_smem, const void *src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dg_smem_u32(dst_smem)), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Likelihood pass of one warp.  The chain's reads are cut into ITEMS of 32 consecutive read
-// pairs of one time point (cum[t] = first item of time t); warp wl of NWL takes a contiguous
-// run of items, so it changes time point (and reloads f) only a few times per pass.
+// pairs of one time point (cum[t] = first item of time t); a warp takes the contiguous run of
+// items [q0, q1) (fixed for the chain), so it changes time point (and reloads f) only a few times per pass.
 //   x_n^(j) = sum_k W[n,k] f^(j)[k]                            model_GP.py:338
 // W block of a time point: isoform-major, row k = npairs double2 (two reads per 16-byte
 // word; consecutive lanes take consecutive words: conflict-free LDS.128 / coalesced
@@ -104,31 +124,43 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // broadcast LDS.128.  prod_n x_n is carried per candidate as a mantissa product and an
 // exponent sum; anything that is not a positive normal double raises `bad` (the round is
 // then redone with real logarithms, LOGPATH).
+// W_STAGED: the warp's ring is a CYCLIC stream over its items -- after the last item of a pass the
+// first items of the NEXT pass are already on their way (every pass reads the same items), so a
+// round does not start with an empty pipeline and the copies overlap the serial part of the round.
+// ring_pos: -1 before the first pass of a chain (the pass primes the ring), then the slot of the
+// next item; the caller drains the ring (cp.async.wait_group 0) when the chain leaves the block.
 template <int KC, int J, int WMODE, bool LOGPATH>
 __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, int Tc, const int *rel, const int *ncnt,
-                                         const int *cum, const double *ff, double *stage, int lane, int wl, int NWL,
-                                         double (&mm)[J], int (&ee)[J], unsigned &bad, double (&ls)[J]) {
+                                         const int *cum, const double *ff, double *stage, int lane, int q0, int q1,
+                                         int &ring_pos, int pin16, double (&mm)[J], int (&ee)[J], unsigned &bad, double (&ls)[J]) {
     constexpr int JP = (J + 1) & ~1;
     constexpr int IW = dg_item_words(KC > 0 ? KC : DG_MAXC), IP = 32 * IW;   // 16-byte words per lane, read pairs per item
     constexpr int kStages = dg_stages(KC > 0 ? KC : DG_MAXC);
-    const int nitems = cum[Tc];
     const int kmax = KC > 0 ? KC : C;
-    const int per = (nitems + NWL - 1) / NWL;
-    const int q0 = min(wl * per, nitems), q1 = min(q0 + per, nitems);
     if (q0 >= q1) return;
     double2 *mystage = reinterpret_cast<double2 *>(stage) + lane;     // [stage][k][word][32 lanes]
     // issue cursor (W_STAGED): item qi of time point ti, lane's first pair ip of inp, source word isrc
     int qi = q0, ti = 0, ip = 0, inp = 0;
     const double2 *isrc = nullptr;
     auto issue = [&](int slot) {
-        if (qi < q1) {
-            if (isrc == nullptr || qi >= cum[ti + 1]) {
-                while (qi >= cum[ti + 1]) ++ti;
-                const int r0 = rel[ti];
-                inp = (rel[ti + 1] - r0) >> 1;
-                ip = (qi - cum[ti]) * IP + lane;
-                isrc = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0) + ip;
+        if (isrc == nullptr || qi >= cum[ti + 1]) {
+            while (qi >= cum[ti + 1]) ++ti;
+            const int r0 = rel[ti];
+            inp = (rel[ti + 1] - r0) >> 1;
+            ip = (qi - cum[ti]) * IP + lane;
+            isrc = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0) + ip;
+        }
+        if (pin16 > 0) {                                                 // uniform: the first pin16/16 of the run stay in L2
+            const uint64_t pol = ((qi - q0) * 16 < pin16 * (q1 - q0)) ? l2_policy_keep() : l2_policy_stream();
+#pragma unroll
+            for (int w = 0; w < IW; ++w) {
+                if (ip + 32 * w < inp) {
+#pragma unroll
+                    for (int k = 0; k < kmax; ++k)
+                        cp_async16_hint(mystage + ((slot * kmax + k) * IW + w) * 32, isrc + 32 * w + (size_t)k * inp, pol);
+                }
             }
+        } else {
 #pragma unroll
             for (int w = 0; w < IW; ++w) {
                 if (ip + 32 * w < inp) {
@@ -137,13 +169,23 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
                         cp_async16(mystage + ((slot * kmax + k) * IW + w) * 32, isrc + 32 * w + (size_t)k * inp);
                 }
             }
-            ++qi; ip += IP; isrc += IP;
         }
+        ++qi; ip += IP; isrc += IP;
+        if (qi == q1) { qi = q0; ti = 0; isrc = nullptr; }               // the stream is cyclic
         cp_async_commit();
     };
+    int islot = 0, cslot = 0;                                        // ring slots of the next issue / the next item
     if (WMODE == W_STAGED) {
+        if (ring_pos < 0) {                                          // first pass of the chain: prime the ring
 #pragma unroll
-        for (int s = 0; s < kStages - 1; ++s) issue(s);
+            for (int s = 0; s < kStages - 1; ++s) issue(s);
+            ring_pos = 0;
+        } else {                                                     // kStages-1 items are in flight: move the cursor past them
+            qi = q0 + (kStages - 1) % (q1 - q0);
+        }
+        cslot = ring_pos;
+        islot = cslot + kStages - 1;
+        if (islot >= kStages) islot -= kStages;
     }
 #ifndef DG_FREG_MAX
 #define DG_FREG_MAX 12
@@ -151,7 +193,6 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
     constexpr bool FREG = (KC > 0 && KC * J <= (J > 3 ? 18 : DG_FREG_MAX));    // f of the time point held in registers
     constexpr int FR = FREG ? KC : 1;
     int it = 0, q = q0, tt = 0;
-    int islot = kStages - 1, cslot = 0;                              // ring slots of the next issue / the next item
     while (q < q1) {
         while (q >= cum[tt + 1]) ++tt;
         const int c0 = cum[tt], c1 = min(cum[tt + 1], q1);
@@ -258,21 +299,21 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
             }
         }
     }
-    if (WMODE == W_STAGED) cp_async_wait<0>();
+    if (WMODE == W_STAGED) ring_pos = cslot;
 }
 
 // Slow path (some x_n is 0 / negative / non-finite): the same sums with real logarithms so
 // that -inf and NaN propagate like np.log(...).sum() does (model_GP.py:344).
 template <int KC, int J, int WMODE>
 __device__ __noinline__ void lik_warp_pass_log(const double *Wc, const int *rel, const int *ncnt, const int *cum,
-                                               const double *ff, double *stage, double *red, int C, int Tc, int NWL,
-                                               int lane, int wl, int slots, int cs) {
+                                               const double *ff, double *stage, double *red, int C, int Tc, int q0, int q1,
+                                               int &ring_pos, int pin16, int lane, int wl, int slots, int cs) {
     double mm[J], ls[J];
     int ee[J];
     unsigned bad = 0u;
 #pragma unroll
     for (int j = 0; j < J; ++j) { mm[j] = 1.0; ls[j] = 0.0; ee[j] = 0; }
-    lik_pass<KC, J, WMODE, true>(Wc, C, Tc, rel, ncnt, cum, ff, stage, lane, wl, NWL, mm, ee, bad, ls);
+    lik_pass<KC, J, WMODE, true>(Wc, C, Tc, rel, ncnt, cum, ff, stage, lane, q0, q1, ring_pos, pin16, mm, ee, bad, ls);
 #pragma unroll
     for (int j = 0; j < J; ++j) {
         double v = ls[j];
@@ -578,8 +619,11 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     double *Wsm = smem + L.w;
     const double prior_const = ct.prior_const[chain];
     const bool is_state = tid < nstate;
-    const int wl = warp - S;                              // likelihood-warp index (>= 0 for those)
-    const int gwl = crank * NWL + wl, GW = cs * NWL;      // ... within the whole cluster
+    // EVERY warp takes part in the likelihood pass: the dedicated likelihood warps (index 0 .. NWL-1) start right
+    // after B1, the state warps (NWL .. nwarps-1) join once the prior terms of the round are done and therefore get
+    // a smaller share of the items (DG_STATE_LIK_WEIGHT sixteenths of a likelihood warp's; 0 = none)
+    const int wl = is_state ? NWL + warp : warp - S;      // likelihood index of this warp within the block
+    const int gwl = crank * nwarps + wl, GW = cs * nwarps;   // ... within the whole cluster
     int xbuf = 0;                                         // exchange buffer (clusters double-buffer)
 
     const int32_t *roff = gt.roff + (size_t)g * (T + 1) + t0;
@@ -589,7 +633,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     const size_t wbytes = (size_t)C * r_total * sizeof(double);
     constexpr bool W_IN_SMEM = (WMODE == W_RESIDENT);
     const double *Wc = W_IN_SMEM ? Wsm : Wg;
-    double *stage = Wsm + (size_t)(wl > 0 ? wl : 0) * dg_stages(KC > 0 ? KC : DG_MAXC) * (dg_stage_slot_bytes(KC > 0 ? KC : DG_MAXC) / 8);   // W_STAGED: per-warp cp.async ring
+    double *stage = Wsm + (size_t)wl * dg_stages(KC > 0 ? KC : DG_MAXC) * (dg_stage_slot_bytes(KC > 0 ? KC : DG_MAXC) / 8);   // W_STAGED: per-warp cp.async ring
 
     // ---- stage W (TMA bulk copy, asynchronous) and the small per-chain constants --------
     if (W_IN_SMEM) {
@@ -686,6 +730,17 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         }
     }
     __syncthreads();
+    // this warp's run of likelihood items: the items of the chain split over all warps of the block (cluster) in
+    // proportion to their weights
+    int lq0, lq1, ring_pos = -1;
+    {
+        const long long wblock = 16ll * NWL + (long long)DG_STATE_LIK_WEIGHT * S, wall_ = wblock * cs;
+        const long long pre = (long long)crank * wblock + (wl < NWL ? 16ll * wl : 16ll * NWL + (long long)DG_STATE_LIK_WEIGHT * (wl - NWL));
+        const long long own = wl < NWL ? 16 : DG_STATE_LIK_WEIGHT;
+        const long long nitems = cum[Tc];
+        lq0 = (int)((nitems * pre) / wall_);
+        lq1 = (int)((nitems * (pre + own)) / wall_);
+    }
 
     const int m_start = m;
     const int m_end = (m_start + n_steps < M) ? (m_start + n_steps) : M;
@@ -787,45 +842,8 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
         }
         __syncthreads();                                                     // B1: f ready
         DG_TICK(0);
-        // ================= likelihood warps || rest of the serial part =================
-        if (!is_state) {
-            double mm[J], lsd[J];
-            int ee[J];
-            unsigned bad = 0u;
-#pragma unroll
-            for (int j = 0; j < J; ++j) { mm[j] = 1.0; ee[j] = 0; lsd[j] = 0.0; }
-            lik_pass<KC, J, WMODE, false>(Wc, C, Tc, rel, ncnt, cum, ff, stage, lane, gwl, GW, mm, ee, bad, lsd);
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int gg = __double2hiint(mm[j]);
-                ee[j] += (gg >> 20) - 1023;
-                mm[j] = dg_mant(mm[j], gg);
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    mm[j] *= __shfl_xor_sync(0xffffffffu, mm[j], off);       // < 2^32
-                    ee[j] += __shfl_xor_sync(0xffffffffu, ee[j], off);
-                }
-                bad |= __shfl_xor_sync(0xffffffffu, bad, off);
-            }
-            if (lane == 0) {
-                double *rd = red + xbuf * J * SLOTS;
-                int *ri = redi + xbuf * J * SLOTS;
-                int *rb = reinterpret_cast<int *>(redb) + xbuf * SLOTS;
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    const int gg = __double2hiint(mm[j]);
-                    const double mv = dg_mant(mm[j], gg);
-                    const int ev = ee[j] + (gg >> 20) - 1023;
-                    if (cs == 1) { rd[j * SLOTS + wl] = mv; ri[j * SLOTS + wl] = ev; }
-                    else for (int r = 0; r < cs; ++r) { st_cluster(rd + j * SLOTS + gwl, r, mv); st_cluster(ri + j * SLOTS + gwl, r, ev); }
-                }
-                if (cs == 1) rb[wl] = (int)bad;
-                else for (int r = 0; r < cs; ++r) st_cluster(rb + gwl, r, (int)bad);
-            }
-        } else {
+        // ================= rest of the serial part (state warps), then the likelihood pass (every warp) ==========
+        if (is_state) {
             if (s_act) {
 #pragma unroll
                 for (int j = 0; j < J; ++j) psic[j * CT + si] = ej[j] / dg_np_sum(ex + j * CT + stt, C, Tc);   // (:335)
@@ -859,6 +877,45 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             }
         }
         DG_TICK(1);
+        {
+            double mm[J], lsd[J];
+            int ee[J];
+            unsigned bad = 0u;
+#pragma unroll
+            for (int j = 0; j < J; ++j) { mm[j] = 1.0; ee[j] = 0; lsd[j] = 0.0; }
+            lik_pass<KC, J, WMODE, false>(Wc, C, Tc, rel, ncnt, cum, ff, stage, lane, lq0, lq1, ring_pos, ct.l2pin, mm, ee, bad, lsd);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int gg = __double2hiint(mm[j]);
+                ee[j] += (gg >> 20) - 1023;
+                mm[j] = dg_mant(mm[j], gg);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    mm[j] *= __shfl_xor_sync(0xffffffffu, mm[j], off);       // < 2^32
+                    ee[j] += __shfl_xor_sync(0xffffffffu, ee[j], off);
+                }
+                bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+            }
+            if (lane == 0) {
+                double *rd = red + xbuf * J * SLOTS;
+                int *ri = redi + xbuf * J * SLOTS;
+                int *rb = reinterpret_cast<int *>(redb) + xbuf * SLOTS;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int gg = __double2hiint(mm[j]);
+                    const double mv = dg_mant(mm[j], gg);
+                    const int ev = ee[j] + (gg >> 20) - 1023;
+                    if (cs == 1) { rd[j * SLOTS + wl] = mv; ri[j * SLOTS + wl] = ev; }
+                    else for (int r = 0; r < cs; ++r) { st_cluster(rd + j * SLOTS + gwl, r, mv); st_cluster(ri + j * SLOTS + gwl, r, ev); }
+                }
+                if (cs == 1) rb[wl] = (int)bad;
+                else for (int r = 0; r < cs; ++r) st_cluster(rb + gwl, r, (int)bad);
+            }
+        }
+        DG_TICK(6);
         if (cs == 1) __syncthreads(); else cluster_barrier();                // B2: partial likelihoods ready
         DG_TICK(2);
         // ================= decisions (warp 0; thread 0 walks the tree) =================
@@ -968,9 +1025,8 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             redo = bc[3] != 0.0;
             if (cs > 1) xbuf ^= 1;
             if (redo) {                                                      // rare: some x_n was not a positive normal
-                if (!is_state)
-                    lik_warp_pass_log<KC, J, WMODE>(Wc, rel, ncnt, cum, ff, stage, red + xbuf * J * SLOTS, C, Tc, GW, lane,
-                                                    gwl, SLOTS, cs);
+                lik_warp_pass_log<KC, J, WMODE>(Wc, rel, ncnt, cum, ff, stage, red + xbuf * J * SLOTS, C, Tc, lq0, lq1,
+                                                ring_pos, ct.l2pin, lane, gwl, SLOTS, cs);
                 if (cs == 1) __syncthreads(); else cluster_barrier();
             }
         } while (redo);
@@ -1050,6 +1106,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
     if (state == 0 && m >= M) { state = DICEGP_CHAIN_EXHAUSTED_; m_ret = M - 1; }
 
     // ---- save state ------------------------------------------------------------------------
+    if (WMODE == W_STAGED) cp_async_wait<0>();            // the copies of the pass that will not run
     __syncthreads();
     if (s_act && lead) { st[si] = y_now; st[CT + si] = psi_now; }
     if (tid == 0) {

@@ -48,6 +48,7 @@
 #define DG_WIDE_SLOTS 8             // ring slots (tasks in flight) per consumer warp
 #define DG_WIDE_MAXCT 128           // latent values (C * Tc) of a chain this kernel takes
 #define DG_WIDE_THREADS 576         // launch bound: 17 warps (16 consumers + aux) or 2 blocks of 9 warps per SM
+#define DG_WIDE_MAXCS 8             // blocks of a thread-block cluster that share one chain
 
 #ifdef DG_PROFILE
 // warp 0 lane 0: 0 S, 1 wait f, 2 likelihood, 3 wait partials, 4 decide + new state, 5 wait state, 6 rows; aux lane 0: 7 busy
@@ -59,7 +60,7 @@
 namespace dg {
 
 struct WideLayout {
-    int state, ycand, ex, pr, ff, priorc, redm, rede, redb, bc, zbuf, dring, kinv, pfac, ijs, jcon, sqs, len, ints, gw, bars;
+    int state, ycand, ex, pr, ff, priorc, redm, rede, redb, xm, xe, xb, bc, zbuf, dring, kinv, pfac, ijs, jcon, sqs, len, ints, gw, bars;
     int ring;                   // doubles before the ring (128-byte aligned)
 };
 
@@ -77,6 +78,10 @@ __host__ __device__ inline WideLayout dg_wide_layout(int C, int Tc, int ncw, int
     L.redm = o; o += ncw * J;
     L.rede = o; o += (ncw * J + 1) / 2;                // ints
     L.redb = o; o += (ncw + 1) / 2;                    // ints
+    // cluster launches: per-block partial likelihoods of the J candidates, exchanged through DSMEM (two buffers)
+    L.xm = o; o += 2 * DG_WIDE_MAXCS * J;
+    L.xe = o; o += DG_WIDE_MAXCS * J;                  // 2 x MAXCS x J ints
+    L.xb = o; o += DG_WIDE_MAXCS;                      // 2 x MAXCS ints
     L.bc = o; o += 96;
     L.zbuf = o; o += 2 * J * RL;
     L.dring = o; o += 2 * J * RL;
@@ -317,15 +322,24 @@ __device__ __forceinline__ void wide_flush(double (&mm)[RJ], int (&ee)[RJ], int 
 // ---------------------------------------------------------------------------------------
 // one chain, up to n_steps steps
 // ---------------------------------------------------------------------------------------
-template <int KC, int RJ>
+// CLUSTER: a thread-block cluster of cs blocks advances ONE chain (the last stragglers of a batch, when there are
+// fewer chains than SMs): every block runs the same serial phases on the same inputs (same bits), the likelihood
+// tasks are split over the consumer warps of all blocks, every block folds its warps' partial products into one
+// (mantissa, exponent) pair per candidate and stores it into the shared memory of all blocks (DSMEM, two buffers),
+// one barrier.cluster per pass over W.  Only the lead block writes trace rows, runs the Geweke rule (its verdict is
+// broadcast through DSMEM) and saves the state; trace pages are pre-assigned by the host.
+template <int KC, int RJ, bool CLUSTER>
 __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const StreamArgs &sa, int chain, int slot_id,
-                               int n_steps, double *smem, int ring_bytes) {
+                               int n_steps, double *smem, int ring_bytes, int cs_rt, int crank_rt) {
     constexpr int J = 4 * RJ, RING = 2 * J;
     constexpr unsigned FULL = 0xffffffffu;
+    const int cs = CLUSTER ? cs_rt : 1, crank = CLUSTER ? crank_rt : 0;
+    const bool lead = crank == 0;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const int NCW = nwarps - 1;
     const bool is_aux = warp == NCW;
+    int xbuf = 0;                                         // exchange buffer of the next DSMEM exchange
 
     const int g = ct.gene[chain], t0 = ct.t0[chain];
     const int C = KC > 0 ? KC : gt.C[g];
@@ -337,6 +351,8 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
     double *kinv = smem + L.kinv, *pfac = smem + L.pfac, *ijs = smem + L.ijs, *jcon = smem + L.jcon, *sqs = smem + L.sqs;
     double *lens = smem + L.len, *gw = smem + L.gw;
     int *rede = reinterpret_cast<int *>(smem + L.rede), *redb = reinterpret_cast<int *>(smem + L.redb);
+    double *xm = smem + L.xm;
+    int *xe = reinterpret_cast<int *>(smem + L.xe), *xb = reinterpret_cast<int *>(smem + L.xb);
     int *rel = reinterpret_cast<int *>(smem + L.ints), *ncnt = rel + (Tc + 1), *cum = ncnt + Tc;
     unsigned long long *mybars = reinterpret_cast<unsigned long long *>(smem + L.bars) + warp * DG_WIDE_SLOTS;
     double2 *ring2 = reinterpret_cast<double2 *>(smem + L.ring);
@@ -370,7 +386,7 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
     double *st = ct.st + ct.st_off[chain];
     const int rowlen = 2 * CT + 2;
     double *gst = st + rowlen;                            // running Geweke sums (geweke_converged)
-    if (m == 0 && tid < 4) gst[tid] = 0.0;
+    if (m == 0 && lead && tid < 4) gst[tid] = 0.0;
     int64_t *ptab = ct.ptab + ct.ptab_off[chain];
     const int pshift = ct.pshift[chain];
     const int pmask = (1 << pshift) - 1;
@@ -399,8 +415,8 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
     __syncthreads();
     // ---- this warp's share of W: a contiguous run of tasks, streamed through its OWN ring of TMA slots ----
     const int NT = cum[Tc];                               // tasks per round
-    const int per = (NT + NCW - 1) / NCW;
-    const int ta = is_aux ? 0 : min(warp * per, NT), tb = is_aux ? 0 : min(ta + per, NT);
+    const int per = (NT + cs * NCW - 1) / (cs * NCW);     // ... split over the consumer warps of the whole cluster
+    const int ta = is_aux ? 0 : min((crank * NCW + warp) * per, NT), tb = is_aux ? 0 : min(ta + per, NT);
     const int ntw = tb - ta;                              // tasks of this warp per round
     const int task_w2 = C * 16;                           // double2 per task (= tile): [isoform][16 words]
     const int warp_ring_w2 = ((ring_bytes / NCW) / 16) & ~7;
@@ -508,6 +524,7 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
         DG_WTICK(1);
         // ================= likelihood (consumer warps) || stream + trace pages (aux warp) =================
         bool redo = false;
+        int xcur = 0;                                                        // buffer of the last DSMEM exchange
         do {
             // the stream rows of the next rounds (ring holds [m, produced) -> up to m + 2J): the normals are made by
             // the consumer warps (one pair per thread) before their likelihood tasks, the rest by the aux warp
@@ -626,9 +643,43 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
             DG_WTICK(2);
             __syncthreads();                                                 // partial likelihoods ready
             DG_WTICK(3);
+            if (CLUSTER && cs > 1) {
+                // fold this block's partials into one (mantissa, exponent) pair -- or, on the log path, one sum -- per
+                // candidate and store it into every block of the cluster; the buffers alternate between exchanges
+                if (warp == 0) {
+                    if (lane < J) {
+                        double v = 0.0;
+                        int e = 0;
+                        if (!redo) {
+                            double ma = 1.0, mb = 1.0;
+                            int w = 0;
+                            for (; w + 1 < NCW; w += 2) { ma *= redm[w * J + lane]; mb *= redm[(w + 1) * J + lane]; e += rede[w * J + lane] + rede[(w + 1) * J + lane]; }
+                            if (w < NCW) { ma *= redm[w * J + lane]; e += rede[w * J + lane]; }
+                            ma *= mb;
+                            const int gq = __double2hiint(ma);
+                            e += (gq >> 20) - 1023;
+                            v = dg_mant(ma, gq);
+                        } else {
+                            for (int w = 0; w < NCW; ++w) v += redm[w * J + lane];
+                        }
+                        double *dm = xm + (xbuf * DG_WIDE_MAXCS + crank) * J + lane;
+                        int *de = xe + (xbuf * DG_WIDE_MAXCS + crank) * J + lane;
+                        for (int r = 0; r < cs; ++r) { st_cluster(dm, (unsigned)r, v); st_cluster(de, (unsigned)r, e); }
+                    }
+                    if (lane == 0) {
+                        int anyb = 0;
+                        if (!redo) for (int w = 0; w < NCW; ++w) anyb |= redb[w];
+                        for (int r = 0; r < cs; ++r) st_cluster(xb + xbuf * DG_WIDE_MAXCS + crank, (unsigned)r, anyb);
+                    }
+                }
+                cluster_barrier();
+                xcur = xbuf;
+                xbuf ^= 1;
+            }
             if (!redo) {
                 int anyb = 0;
-                for (int w = 0; w < NCW; ++w) anyb |= redb[w];
+                if (CLUSTER && cs > 1) { for (int r = 0; r < cs; ++r) anyb |= xb[xcur * DG_WIDE_MAXCS + r]; }
+                else { for (int w = 0; w < NCW; ++w) anyb |= redb[w]; }
                 if (anyb) { redo = true; __syncthreads(); continue; }        // rare: some x_n was not a positive normal
             }
             break;
@@ -639,7 +690,20 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
         const int nd_ok = init ? 0 : (int)bc[8];
         double lik = 0.0, P_try = 0.0;
         if (lane < J) {
-            if (!redo) {
+            if (CLUSTER && cs > 1) {
+                const double *pm = xm + xcur * DG_WIDE_MAXCS * J + lane;
+                const int *pe = xe + xcur * DG_WIDE_MAXCS * J + lane;
+                if (!redo) {
+                    double ma = 1.0;
+                    int e = 0;
+                    for (int r = 0; r < cs; ++r) { ma *= pm[r * J]; e += pe[r * J]; }          // <= 8 mantissas: < 2^8
+                    const int gq = __double2hiint(ma);
+                    e += (gq >> 20) - 1023;
+                    lik = fma((double)e, 0.693147180559945309417232121458, log(dg_mant(ma, gq)));
+                } else {
+                    for (int r = 0; r < cs; ++r) lik += pm[r * J];
+                }
+            } else if (!redo) {
                 double ma = 1.0, mb = 1.0;
                 int e = 0;
                 int w = 0;
@@ -693,7 +757,7 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
         DG_WTICK(4);
         __syncthreads();                                                     // new state visible; candidates free
         DG_WTICK(5);
-        if (nd > 0) {
+        if (nd > 0 && lead) {
             const double *sold = state + cur * 2 * CT, *snw = state + (cur ^ 1) * 2 * CT;
             const int total = nd * rowlen;
             for (int idx = tid; idx < total; idx += nthreads) {
@@ -719,7 +783,17 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
         const int mlast = m - 1;
         if (nd > 0 && mlast >= initial && (mlast % gap) == 0) {
             __syncthreads();                                                 // the rows are visible
-            const int conv = geweke_converged(gw, gst, CTm, nwarps, warp, lane, tv, mlast);
+            int conv;
+            if (CLUSTER && cs > 1) {                                         // the lead block decides for the cluster
+                if (lead) {
+                    conv = geweke_converged(gw, gst, CTm, nwarps, warp, lane, tv, mlast);
+                    if (tid == 0) for (int r = 0; r < cs; ++r) st_cluster(bc + 9, (unsigned)r, (double)conv);
+                }
+                cluster_barrier();
+                conv = (int)bc[9];
+            } else {
+                conv = geweke_converged(gw, gst, CTm, nwarps, warp, lane, tv, mlast);
+            }
             if (conv) {
                 state_code = DICEGP_CHAIN_CONVERGED_;
                 m_ret = mlast;
@@ -747,14 +821,14 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
             for (int s2 = 0; s2 < SL; ++s2) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(dg_smem_u32(mybars + s2)) : "memory");
     }
     __syncthreads();
-    {
+    if (lead) {
         const double *snow = state + cur * 2 * CT;
         for (int i = tid; i < CT; i += nthreads) { st[i] = snow[CT + i]; st[CT + i] = snow[i]; }
     }
     if (lane == 0 && ct.ctr) {
         if (tma_bytes) atomicAdd(ct.ctr + 0, tma_bytes);
     }
-    if (tid == 0) {
+    if (tid == 0 && lead) {
         st[2 * CT] = P_now; st[2 * CT + 1] = L_now;
         ct.m_next[chain] = m;
         ct.cnt[chain] = cnt;
@@ -773,25 +847,39 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
 
 }  // namespace dg
 
-// Persistent blocks pull chains from `queue` (device-stream runs) or block b advances chain ids[b].
+// Persistent blocks (clusters) pull chains from `queue` (device-stream runs) or block (cluster) b advances chain ids[b].
 // ring_bytes: shared memory behind the largest fixed part of the launch's chains, for the W ring.
-template <int KC, int RJ>
+template <int KC, int RJ, bool CLUSTER = false>
 __global__ void __launch_bounds__(DG_WIDE_THREADS, 1)
 dicegp_wide_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__restrict__ ids, int n_ids, int n_steps,
                    int ring_bytes, int *queue) {
     extern __shared__ __align__(128) double dg_smem[];
     __shared__ int next_slot;
-    int slot = blockIdx.x;
+    const int cs = CLUSTER ? (int)dg::cluster_size() : 1, crank = CLUSTER ? (int)dg::cluster_rank() : 0;
+    int slot = blockIdx.x / cs;
     while (true) {
         if (queue != nullptr) {
-            if (threadIdx.x == 0) next_slot = atomicAdd(queue, 1);
-            __syncthreads();
-            slot = next_slot;
-            __syncthreads();
+            if (cs == 1) {
+                if (threadIdx.x == 0) next_slot = atomicAdd(queue, 1);
+                __syncthreads();
+                slot = next_slot;
+                __syncthreads();
+            } else {
+                if (crank == 0 && threadIdx.x == 0) {
+                    const int sl = atomicAdd(queue, 1);
+                    for (int r = 0; r < cs; ++r) dg::st_cluster(&next_slot, (unsigned)r, sl);
+                }
+                dg::cluster_barrier();
+                slot = next_slot;
+                dg::cluster_barrier();
+            }
         }
         if (slot >= n_ids) break;
-        if (ct.state[ids[slot]] == 0) dg::run_chain_wide<KC, RJ>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, ring_bytes);
-        __syncthreads();
+        // every block of the cluster reads the chain state BEFORE the lead block may change it
+        const bool running = ct.state[ids[slot]] == 0;
+        if (cs > 1) dg::cluster_barrier();
+        if (running) dg::run_chain_wide<KC, RJ, CLUSTER>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, ring_bytes, cs, crank);
+        if (cs == 1) __syncthreads(); else dg::cluster_barrier();
         if (queue == nullptr) break;
     }
 }

@@ -257,6 +257,19 @@ def test_straggler_pass_resumes_device_stream_bit_identically(ctx, monkeypatch):
     check_main(out, inputs, 1150, 1000, 50)
 
 
+@pytest.mark.parametrize("cs", ["8", "2"])
+def test_last_stragglers_on_clusters_step_parity(ctx, monkeypatch, cs):
+    """Three passes: throughput shapes, one chain per SM (wide-round kernel), then the wide-round kernel on
+    thread-block clusters (every chain split over `cs` SMs, partial likelihoods exchanged through DSMEM,
+    lead block writes the trace and runs the Geweke rule): same step parity with the oracle."""
+    monkeypatch.setenv("DICEGP_STRAGGLER_STEPS", "450,700")
+    monkeypatch.setenv("DICEGP_WIDE_CS", cs)
+    genes = [540, 541, 542, 543]
+    inputs = [synth.gene_matrices("timeseries", g, reads=300, T=4, C=C) for g, C in zip(genes, (2, 3, 5, 8))]
+    out = run_pipeline(ctx, inputs, genes, seed=47, M=1250, initial=1000, gap=50)
+    check_main(out, inputs, 1250, 1000, 50)
+
+
 def test_cluster_tier_device_stream_step_parity(ctx):
     """A gene whose W (1.3 MB) takes the thread-block-cluster tier, device-stream mode."""
     genes = [530]
