@@ -424,11 +424,11 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
     const int cap = warp_ring_w2 / task_w2;               // tasks the ring holds
     const bool resident = ntw <= cap;                     // all of them: loaded once, one barrier, one copy
     // streaming: chunks of G consecutive tasks (one bulk copy each: the tiles of a gene are contiguous), SL slots
-    const int G = resident ? max(ntw, 1) : max(1, min(4, cap / 4));
+    const int G = resident ? max(ntw, 1) : max(1, min(4, cap / 2));
     const int SL = resident ? 1 : min(cap / G, DG_WIDE_SLOTS);
     const int NC = (ntw + G - 1) / G;                     // chunks per round
     const double2 *mysrc = reinterpret_cast<const double2 *>(gt.Wt + gt.wtoff[g]) + (size_t)(toffg[0] + ta) * task_w2;
-    unsigned long long tma_bytes = 0;
+    unsigned long long tma_chunks = 0;                    // bulk copies issued by this warp (lane 0)
     // chunk `c` of this warp's run into ring slot `slot`: ONE bulk copy, issued by lane 0
     auto issue_chunk = [&](int c, int slot) {
         if (lane == 0) {
@@ -440,7 +440,7 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                 ::"r"(dg_smem_u32(myring + (size_t)slot * G * task_w2)), "l"(mysrc + (size_t)first * task_w2), "r"(bytes), "r"(bar)
                 : "memory");
-            tma_bytes += bytes;
+            ++tma_chunks;
         }
     };
     if (!is_aux && ntw > 0) {
@@ -451,7 +451,9 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
         __syncwarp();
         for (int i = 0; i < SL; ++i) issue_chunk(i % NC, i);
     }
-    int qc = 0;                                           // chunks consumed so far by this warp (slot = qc % SL)
+    // ring cursor, kept as running counters (no divisions in the loop): slot and mbarrier phase of the next chunk
+    // this warp consumes, and the index of the chunk that will be issued into the slot it frees
+    int rslot = 0, rphase = 0, cnext = SL % max(NC, 1);
 
     const int m_start = m;
     const int m_end = (m_start + n_steps < M) ? (m_start + n_steps) : M;
@@ -549,11 +551,11 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
                 for (int n = 0; n < RJ; ++n) { mm[n] = 1.0; ee[n] = 0; ls[n] = 0.0; }
                 int tt = 0, it = 0;
                 for (int c = 0; c < NC; ++c) {
-                    const int slot = resident ? 0 : qc % SL;
+                    const int slot = resident ? 0 : rslot;
 #ifdef DG_PROFILE
                     long long lt0 = clock64();
 #endif
-                    mbar_wait(dg_smem_u32(mybars + slot), resident ? 0u : (uint32_t)((qc / SL) & 1));
+                    mbar_wait(dg_smem_u32(mybars + slot), resident ? 0u : (uint32_t)rphase);
 #ifdef DG_PROFILE
                     long long lt1 = clock64();
                     if (lane == 0 && warp == 0) wprof[8] += lt1 - lt0;
@@ -586,8 +588,9 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
                         // the slot is free: refill it with the chunk SL ahead (the sequence repeats every round, so the
                         // first chunks of the next round are on their way while this round decides)
                         __syncwarp();
-                        issue_chunk((c + SL) % NC, slot);
-                        ++qc;
+                        issue_chunk(cnext, slot);
+                        if (++cnext == NC) cnext = 0;
+                        if (++rslot == SL) { rslot = 0; rphase ^= 1; }
 #ifdef DG_PROFILE
                         if (lane == 0 && warp == 0) wprof[13] += clock64() - lt2;
 #endif
@@ -815,7 +818,10 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
     // ---- drain the ring (copies in flight into shared memory), save state ----
     if (!is_aux && ntw > 0) {
         if (resident) mbar_wait(dg_smem_u32(mybars), 0u);
-        else for (int q = qc; q < qc + SL; ++q) mbar_wait(dg_smem_u32(mybars + q % SL), (uint32_t)((q / SL) & 1));
+        else for (int q = 0; q < SL; ++q) {                   // the SL chunks in flight, oldest first
+            mbar_wait(dg_smem_u32(mybars + rslot), (uint32_t)rphase);
+            if (++rslot == SL) { rslot = 0; rphase ^= 1; }
+        }
         __syncwarp();
         if (lane == 0)
             for (int s2 = 0; s2 < SL; ++s2) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(dg_smem_u32(mybars + s2)) : "memory");
@@ -826,7 +832,9 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
         for (int i = tid; i < CT; i += nthreads) { st[i] = snow[CT + i]; st[CT + i] = snow[i]; }
     }
     if (lane == 0 && ct.ctr) {
-        if (tma_bytes) atomicAdd(ct.ctr + 0, tma_bytes);
+        // whole runs of NC chunks (ntw tasks) plus the first chunks (G tasks each) of the run that was cut
+        if (tma_chunks) atomicAdd(ct.ctr + 0, ((tma_chunks / NC) * (unsigned long long)ntw + (tma_chunks % NC) * (unsigned long long)G) *
+                                                  (unsigned long long)task_w2 * 16ull);
     }
     if (tid == 0 && lead) {
         st[2 * CT] = P_now; st[2 * CT + 1] = L_now;
