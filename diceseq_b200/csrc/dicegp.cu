@@ -720,24 +720,27 @@ int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain, int
 }
 
 // ---- wide-round kernel (dicegp_wide.cuh): launch shape per isoform count ----------------------
-struct WidePlan { int ncw, bps, rj; };
+struct WidePlan { int ncw, npw, bps, rj; };
 inline int env_int(const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; }
-WidePlan wide_plan(int C, int latency_mode) {
-    // 16 consumer warps on a whole SM for wide genes (their W then stays L2 resident: 148 x <= 512 KB)
-    // and in the straggler pass; two blocks of 8 consumer warps per SM for narrow genes (the serial part of
-    // one chain's round overlaps the likelihood pass of the other).  DICEGP_WIDE_NCW / _BPS / _RJ override.
-    static const int e_ncw = env_int("DICEGP_WIDE_NCW", 0), e_bps = env_int("DICEGP_WIDE_BPS", 0), e_rj = env_int("DICEGP_WIDE_RJ", 0);
+WidePlan wide_plan(int C, int cs = 1) {
+    // One block per SM.  16 consumer warps + 2 producer warps for a whole chain (the stream of the ~13 steps a
+    // round commits costs one warp ~55k cycles, about as long as the likelihood pass of a C = 8 chain); on a
+    // cluster the likelihood pass shrinks with the cluster size while the stream does not: 12 consumers + 6
+    // producers.  DICEGP_WIDE_NCW / _NPW / _BPS override.
+    static const int e_ncw = env_int("DICEGP_WIDE_NCW", 0), e_bps = env_int("DICEGP_WIDE_BPS", 0), e_npw = env_int("DICEGP_WIDE_NPW", 0);
     WidePlan p;
     p.rj = 4;
-    (void)latency_mode; (void)C; (void)e_rj;
-    p.ncw = 16; p.bps = 1;
-    if (e_ncw > 0) p.ncw = std::min(e_ncw, DG_WIDE_THREADS / 32 - 1);
+    (void)C;
+    p.ncw = cs > 1 ? 12 : 16; p.npw = cs > 1 ? 6 : 2; p.bps = 1;
+    if (e_ncw > 0) p.ncw = e_ncw;
+    if (e_npw > 0) p.npw = e_npw;
+    if (32 * (p.ncw + p.npw) > DG_WIDE_THREADS) p.ncw = DG_WIDE_THREADS / 32 - p.npw;
     if (e_bps > 0) p.bps = e_bps;
-    if (32 * (p.ncw + 1) * p.bps > DG_WIDE_THREADS) p.bps = std::max(1, DG_WIDE_THREADS / (32 * (p.ncw + 1)));
+    if (32 * (p.ncw + p.npw) * p.bps > DG_WIDE_THREADS) p.bps = std::max(1, DG_WIDE_THREADS / (32 * (p.ncw + p.npw)));
     return p;
 }
 inline size_t wide_fixed_bytes(int C, int Tc, const WidePlan &p) {
-    return (size_t)dg::dg_wide_layout(C, Tc, p.ncw, 4 * p.rj).ring * sizeof(double);
+    return (size_t)dg::dg_wide_layout(C, Tc, p.ncw, 4 * p.rj, p.npw).ring * sizeof(double);
 }
 inline size_t wide_budget(const dicegp_ctx *c, const WidePlan &p) {
     return std::min<size_t>(233472 / p.bps - 1024, c->smem_optin - c->static_smem_wide);
@@ -752,12 +755,12 @@ bool wide_eligible(const dicegp_ctx *c, int chain, int latency_mode) {
     const dicegp_chain_desc &d = c->hdesc[chain];
     const int C = c->hC[d.gene];
     if (C < 2 || C * d.Tc > DG_WIDE_MAXCT) return false;
-    const WidePlan p = wide_plan(C, latency_mode);
+    const WidePlan p = wide_plan(C);
     const size_t stage = (size_t)p.ncw * C * 256;
     return wide_fixed_bytes(C, d.Tc, p) + 2 * stage <= wide_budget(c, p);
 }
 
-typedef void (*wide_kernel_t)(GeneTab, ChainTab, StreamArgs, const int32_t *, int, int, int, int *);
+typedef void (*wide_kernel_t)(GeneTab, ChainTab, StreamArgs, const int32_t *, int, int, int, int, int *);
 wide_kernel_t wide_kernel_for(int kind, bool cluster) {
     if (cluster) {
         switch (kind) {
@@ -852,7 +855,7 @@ int wide_cluster_capacity(dicegp_ctx *c, int cs) {
         int n = 0;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3(c->sm_count / cs * cs); cfg.blockDim = dim3(DG_WIDE_THREADS - 32); cfg.dynamicSmemBytes = smem;
+        cfg.gridDim = dim3(c->sm_count / cs * cs); cfg.blockDim = dim3(DG_WIDE_THREADS); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -982,7 +985,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             if (tier == kWideTier) {
                 int maxC = 2;
                 for (int32_t id : by_group[k]) maxC = std::max(maxC, c->hC[c->hdesc[id].gene]);
-                const WidePlan wp = wide_plan(kind == 0 ? maxC : kind + 1, latency_mode);
+                const WidePlan wp = wide_plan(kind == 0 ? maxC : kind + 1, wide_cs);
                 size_t fixed = 0;
                 for (int32_t id : by_group[k]) {
                     const dicegp_chain_desc &d = c->hdesc[id];
@@ -1015,18 +1018,18 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                     if (rc != DICEGP_OK) return rc;
                 }
                 if (getenv("DICEGP_VERBOSE"))
-                    fprintf(stderr, "[dicegp]   launch wide C-kind %d: %d chains, %d threads, cluster %d, %zu B smem, grid %d\n",
-                            kind == 0 ? 0 : kind + 1, n_ids, 32 * (wp.ncw + 1), wcs, smem, grid);
+                    fprintf(stderr, "[dicegp]   launch wide C-kind %d: %d chains, %d + %d warps, cluster %d, %zu B smem, grid %d\n",
+                            kind == 0 ? 0 : kind + 1, n_ids, wp.ncw, wp.npw, wcs, smem, grid);
                 {
                     cudaLaunchConfig_t cfg;
                     memset(&cfg, 0, sizeof cfg);
-                    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * (wp.ncw + 1)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+                    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * (wp.ncw + wp.npw)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
                     cudaLaunchAttribute attr[1];
                     attr[0].id = cudaLaunchAttributeClusterDimension;
                     attr[0].val.clusterDim.x = wcs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
                     cfg.attrs = attr; cfg.numAttrs = wcs > 1 ? 1 : 0;
                     const int32_t *ids_arg = c->dids.p + base[k];
-                    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, gt, ct, sak, ids_arg, n_ids, n_steps, (int)ring_bytes, queue);
+                    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, gt, ct, sak, ids_arg, n_ids, n_steps, (int)ring_bytes, wp.npw, queue);
                     if (e == cudaSuccess) e = cudaGetLastError();
                     if (e != cudaSuccess) return c->cuda_fail(e, "wide chain kernel launch");
                 }

@@ -12,7 +12,7 @@
 // average p = 0.16, 12 for the slow chains at p = 0.04.  Arithmetic per committed step is that of
 // sequential execution.
 //
-// One block = NCW consumer warps + 1 auxiliary warp; every consumer warp does every phase:
+// One block = NCW consumer warps + 1..6 producer ("auxiliary") warps; every consumer warp does every phase:
 //   S      two sub-phases over all threads: item (j, c, t): candidate y -> exp and its GP-prior term; then
 //          item (j, c, t): length-weighted softmax f[t][c][j], item (j, c): prior of one isoform
 //   LIK    reads in TASKS of 16 words (32 reads) of one time point.  W is read from a TILED copy (GeneTab::Wt,
@@ -64,7 +64,7 @@ struct WideLayout {
     int ring;                   // doubles before the ring (128-byte aligned)
 };
 
-__host__ __device__ inline WideLayout dg_wide_layout(int C, int Tc, int ncw, int J) {
+__host__ __device__ inline WideLayout dg_wide_layout(int C, int Tc, int ncw, int J, int npw = 1) {
     WideLayout L;
     const int CT = C * Tc, RL = CT + 2, ctm = CT - Tc;
     int o = 0;
@@ -90,8 +90,8 @@ __host__ __device__ inline WideLayout dg_wide_layout(int C, int Tc, int ncw, int
     L.ijs = o; o += C; L.jcon = o; o += C; L.sqs = o; o += C;
     L.len = o; o += CT;
     L.ints = o; o += (3 * (Tc + 1) + 1) / 2 + 1;       // rel[Tc+1], ncnt[Tc], cum[Tc+1]
-    L.gw = o; o += 2 * (ncw + 1) * (ctm < DG_GW_COLS ? (ctm > 0 ? ctm : 1) : DG_GW_COLS);
-    L.bars = o; o += (ncw + 1) * DG_WIDE_SLOTS;                   // per consumer warp: one mbarrier per ring slot
+    L.gw = o; o += 2 * (ncw + npw) * (ctm < DG_GW_COLS ? (ctm > 0 ? ctm : 1) : DG_GW_COLS);
+    L.bars = o; o += (ncw + npw) * DG_WIDE_SLOTS;                 // per consumer warp: one mbarrier per ring slot
     o = (o + 15) & ~15;
     L.ring = o;
     return L;
@@ -132,8 +132,14 @@ __device__ __forceinline__ double dg_np_sum_fn(F v, int n) {
 // Stream rows of steps [s0, s1), s1 - s0 <= 2J, into the ring (row = step % RING): the arithmetic of
 // dg::produce_stream (same Philox counters, Box-Muller pairing, z @ A_K accumulated j ascending with fma,
 // Q from -delta).  Called by `nprod` threads (index pt) that synchronise through SYNC().
+// BLOCK: all threads of the block produce (start-up); else the `nprod` threads of the producer warps: one warp
+// synchronises with __syncwarp, several through named barrier 2
 template <bool BLOCK>
-__device__ __forceinline__ void wide_sync() { if (BLOCK) __syncthreads(); else __syncwarp(); }
+__device__ __forceinline__ void wide_sync(int nprod) {
+    if (BLOCK) __syncthreads();
+    else if (nprod <= 32) __syncwarp();
+    else dg_bar(2, nprod);
+}
 
 // The Philox / Box-Muller normals of steps [s0, s1) into zbuf rows 0 .. s1-s0 (one item per pair: ~150 dependent
 // fp64 operations, so the items are spread over as many threads as there are).
@@ -160,7 +166,7 @@ __device__ __noinline__ void wide_produce(bool dev_stream, int s0, int s1, int p
         if (!have_z) wide_normals(s0, s1, pt, nprod, zbuf, C, Tc, seed, sid);
         for (int ds = pt; ds < ns; ds += nprod)
             dring[((s0 + ds) % RING) * RL + CT] = dg_log(dg_uniform(seed, sid, (uint32_t)(s0 + ds)));
-        wide_sync<BLOCK>();
+        wide_sync<BLOCK>(nprod);
         for (int q = pt; q < ns * CTm; q += nprod) {
             const int ds = q / CTm, i = q - ds * CTm;
             const int c = i / Tc, t = i - c * Tc;
@@ -177,7 +183,7 @@ __device__ __noinline__ void wide_produce(bool dev_stream, int s0, int s1, int p
         for (int ds = pt; ds < ns; ds += nprod)
             dring[((s0 + ds) % RING) * RL + CT] = dg_log(ublk[s0 + ds - m_start]);
     }
-    wide_sync<BLOCK>();
+    wide_sync<BLOCK>(nprod);
     for (int q = pt; q < ns * CTm; q += nprod) {                   // per (step, c, t): (d K^-1)[t]
         const int ds = q / CTm, i = q - ds * CTm;
         const int c = i / Tc, t = i - c * Tc;
@@ -186,7 +192,7 @@ __device__ __noinline__ void wide_produce(bool dev_stream, int s0, int s1, int p
         for (int j = 0; j < Tc; ++j) r = fma(d[j], kinv[j * Tc + t], r);
         zbuf[ds * RL + i] = r;                                     // the normals are consumed
     }
-    wide_sync<BLOCK>();
+    wide_sync<BLOCK>(nprod);
     for (int q = pt; q < ns * (C - 1); q += nprod) {               // per (step, c): d K^-1 d -> proposal log-density term
         const int ds = q / (C - 1), c = q - ds * (C - 1);
         const double *d = dring + ((s0 + ds) % RING) * RL + c * Tc;
@@ -195,13 +201,13 @@ __device__ __noinline__ void wide_produce(bool dev_stream, int s0, int s1, int p
         for (int t = 0; t < Tc; ++t) acc = fma(rr[t], d[t], acc);
         rr[0] = jcon[c] - (acc * ijs[c]) / 2.0;
     }
-    wide_sync<BLOCK>();
+    wide_sync<BLOCK>(nprod);
     for (int ds = pt; ds < ns; ds += nprod) {
         double Q = 0.0;
         for (int c = 0; c < C - 1; ++c) Q += zbuf[ds * RL + c * Tc];
         dring[((s0 + ds) % RING) * RL + CT + 1] = Q;
     }
-    wide_sync<BLOCK>();
+    wide_sync<BLOCK>(nprod);
 }
 
 // One task: 16 words (32 reads) of one time point, RJ candidates per lane.
@@ -330,22 +336,25 @@ __device__ __forceinline__ void wide_flush(double (&mm)[RJ], int (&ee)[RJ], int 
 // broadcast through DSMEM) and saves the state; trace pages are pre-assigned by the host.
 template <int KC, int RJ, bool CLUSTER>
 __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const StreamArgs &sa, int chain, int slot_id,
-                               int n_steps, double *smem, int ring_bytes, int cs_rt, int crank_rt) {
+                               int n_steps, double *smem, int ring_bytes, int npw, int cs_rt, int crank_rt) {
     constexpr int J = 4 * RJ, RING = 2 * J;
     constexpr unsigned FULL = 0xffffffffu;
     const int cs = CLUSTER ? cs_rt : 1, crank = CLUSTER ? crank_rt : 0;
     const bool lead = crank == 0;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-    const int NCW = nwarps - 1;
-    const bool is_aux = warp == NCW;
+    // warps [0, NCW) consume W; warps [NCW, nwarps) produce the stream of the next rounds (the first of them also
+    // reserves the trace pages)
+    const int NCW = nwarps - npw;
+    const bool is_aux = warp >= NCW;
+    const bool aux0 = warp == NCW;
     int xbuf = 0;                                         // exchange buffer of the next DSMEM exchange
 
     const int g = ct.gene[chain], t0 = ct.t0[chain];
     const int C = KC > 0 ? KC : gt.C[g];
     const int Tc = ct.Tc[chain], T = gt.T;
     const int CT = C * Tc, CTm = (C - 1) * Tc, RL = CT + 2, CTP = CT | 1;
-    const WideLayout L = dg_wide_layout(C, Tc, NCW, J);
+    const WideLayout L = dg_wide_layout(C, Tc, NCW, J, npw);
     double *state = smem + L.state, *ycand = smem + L.ycand, *ex = smem + L.ex, *pr = smem + L.pr, *ff = smem + L.ff;
     double *priorc = smem + L.priorc, *redm = smem + L.redm, *bc = smem + L.bc, *zbuf = smem + L.zbuf, *dring = smem + L.dring;
     double *kinv = smem + L.kinv, *pfac = smem + L.pfac, *ijs = smem + L.ijs, *jcon = smem + L.jcon, *sqs = smem + L.sqs;
@@ -620,7 +629,7 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
                 const long long at0 = clock64();
 #endif
                 if (!redo) {
-                    if (lane == 0) {
+                    if (aux0 && lane == 0) {
                         // trace pages of the rows this round may write (first touch allocates)
                         int nd_ok = nd_max;
                         for (int d = 0; d < nd_max; ++d) {
@@ -635,12 +644,12 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
                     __syncwarp();
                     if (top_up) {
                         dg_bar(1, nthreads);                                 // normals in zbuf
-                        wide_produce<false>(dev_stream, produced, target, lane, 32, zbuf, dring, RING, C, Tc, pfac, sqs, kinv,
-                                            jcon, ijs, sa.seed, sid, dblk, ublk, m_start, true);
+                        wide_produce<false>(dev_stream, produced, target, tid - NCW * 32, npw * 32, zbuf, dring, RING, C, Tc, pfac, sqs,
+                                            kinv, jcon, ijs, sa.seed, sid, dblk, ublk, m_start, true);
                     }
                 }
 #ifdef DG_PROFILE
-                if (lane == 0) wprof[7] += clock64() - at0;
+                if (aux0 && lane == 0) wprof[7] += clock64() - at0;
 #endif
             }
             DG_WTICK(2);
@@ -807,7 +816,7 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
     }
     if (state_code == 0 && m >= M) { state_code = DICEGP_CHAIN_EXHAUSTED_; m_ret = M - 1; }
 #ifdef DG_PROFILE
-    if (lane == 0 && (warp == 0 || is_aux) && sa.prof) {
+    if (lane == 0 && (warp == 0 || aux0) && sa.prof) {
         unsigned long long *o = reinterpret_cast<unsigned long long *>(const_cast<double *>(sa.prof));
         for (int i = 0; i < 10; ++i) if (wprof[i]) atomicAdd(o + i, (unsigned long long)wprof[i]);
         for (int i = 12; i < 16; ++i) if (wprof[i]) atomicAdd(o + i, (unsigned long long)wprof[i]);
@@ -860,7 +869,7 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
 template <int KC, int RJ, bool CLUSTER = false>
 __global__ void __launch_bounds__(DG_WIDE_THREADS, 1)
 dicegp_wide_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__restrict__ ids, int n_ids, int n_steps,
-                   int ring_bytes, int *queue) {
+                   int ring_bytes, int npw, int *queue) {
     extern __shared__ __align__(128) double dg_smem[];
     __shared__ int next_slot;
     const int cs = CLUSTER ? (int)dg::cluster_size() : 1, crank = CLUSTER ? (int)dg::cluster_rank() : 0;
@@ -886,7 +895,7 @@ dicegp_wide_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__rest
         // every block of the cluster reads the chain state BEFORE the lead block may change it
         const bool running = ct.state[ids[slot]] == 0;
         if (cs > 1) dg::cluster_barrier();
-        if (running) dg::run_chain_wide<KC, RJ, CLUSTER>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, ring_bytes, cs, crank);
+        if (running) dg::run_chain_wide<KC, RJ, CLUSTER>(gt, ct, sa, ids[slot], slot, n_steps, dg_smem, ring_bytes, npw, cs, crank);
         if (cs == 1) __syncthreads(); else dg::cluster_barrier();
         if (queue == nullptr) break;
     }
