@@ -123,18 +123,24 @@ class ClockSampler:
         self.rows = []
 
     def _poll_nvml(self):
+        # The constant (max clock) is asked once; a poll is two cheap queries every 200 ms.  (NVML queries take driver
+        # locks: polled every 100 ms with three queries each, single host-side CUDA calls of the timed steps were
+        # seen to stall for 50-80 ms once or twice per run.)
         nv, h = self.nvml
         bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
                 nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
         while not self._stop.is_set():
             try:
                 sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
                 mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 self.rows.append([str(sm), str(mx)] + ["Active" if mask & b else "Not Active" for b in bits])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.2)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -474,8 +480,10 @@ def run_ours(args, wl):
         clocks.start()
     clocks.mark()
     gathered = [None]
+    step_ms = []                                        # this rank's sample() wall per resident step (diagnostic)
 
     def on_step(k, res):
+        step_ms.append(round(sampler.stats.get("sample_ms", 0.0), 1))
         gathered[0] = partition.gather_batch(res, gene_ids, device=local)    # the final gather (rank 0 gets all genes)
         if rank == 0:
             st_ = sampler.stats
@@ -495,6 +503,10 @@ def run_ours(args, wl):
     total_genes = G * args.steps
     if rank == 0 and world > 1:
         assert gathered[0] is not None and len(gathered[0]["gene_ids"]) == G, "the gather did not return every gene"
+    rank_ms = [step_ms]
+    if world > 1:                                       # outside the timed region: every rank's own step times
+        rank_ms = [None] * world
+        dist.all_gather_object(rank_ms, step_ms)
     conv = sum_over_ranks(float((res.state == 1).sum())) / G
     m_med = float(np.median(gathered[0]["m"])) if rank == 0 else 0.0
     main_ms = max_over_ranks(tot["main_kernel_ms"])
@@ -566,7 +578,8 @@ def run_ours(args, wl):
         "config": result_config(wl),
         "details": {"genes": G, "genes_on_rank0": int(len(gene_ids)), "partition": "LPT greedy on C x reads, final gather of the summaries on rank 0" if world > 1 else "single GPU",
                     "stream": args.stream, "l2": "inputs larger than L2 (%.2f GB of W on rank 0), no flush" % (packed.w_bytes / 1e9),
-                    "converged_fraction": conv, "median_m": m_med},
+                    "converged_fraction": conv, "median_m": m_med,
+                    "rank_sample_ms": rank_ms},
         "clocks": clk,
         "e2e": {"value": e2e_total / (e2e_ms * 1e-3), "unit": "evals/s", "genes_per_s": total_genes / (e2e_ms * 1e-3),
                 "ms_per_step": e2e_ms / args.steps,

@@ -788,28 +788,40 @@ wide_kernel_t wide_kernel_for(int kind, bool cluster) {
 
 // Chains that run on a cluster never allocate trace pages on the device (only the lead block
 // writes the trace, and the blocks must stay in lockstep): give them all their pages now.
-int preallocate_trace_pages(dicegp_ctx *c, const std::vector<int32_t> &ids) {
+int preallocate_trace_pages(dicegp_ctx *c, const std::vector<int32_t> &ids, bool quiet = false) {
     unsigned long long head = 0;
     DG_CUDA(c, cudaMemcpy(&head, c->cpool_head.p, sizeof head, cudaMemcpyDeviceToHost));
-    for (int32_t id : ids) {
+    std::vector<std::vector<int64_t>> tabs(ids.size());
+    unsigned long long need_all = 0;
+    for (size_t i = 0; i < ids.size(); ++i) {                   // first see whether the pool has room for all of them
+        const int32_t id = ids[i];
         const dicegp_chain_desc &d = c->hdesc[id];
         const int64_t rowlen = 2 * (int64_t)c->hC[d.gene] * d.Tc + 2;
         const int shift = c->hpshift[id];
         const int n_pages = (d.M + (1 << shift) - 1) >> shift;
-        std::vector<int64_t> tab(n_pages);
-        DG_CUDA(c, cudaMemcpy(tab.data(), c->cptab.p + c->hptab_off[id], n_pages * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        tabs[i].resize(n_pages);
+        DG_CUDA(c, cudaMemcpy(tabs[i].data(), c->cptab.p + c->hptab_off[id], n_pages * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        for (int p = 0; p < n_pages; ++p)
+            if (tabs[i][p] < 0) need_all += (unsigned long long)rowlen << shift;
+    }
+    if (head + need_all > (unsigned long long)c->pool_cap) {
+        if (quiet) return DICEGP_ERR_NOMEM;
+        return c->fail(DICEGP_ERR_NOMEM, "trace pool too small for the large genes of this batch; raise the trace budget");
+    }
+    for (size_t i = 0; i < ids.size(); ++i) {
+        const int32_t id = ids[i];
+        const dicegp_chain_desc &d = c->hdesc[id];
+        const int64_t rowlen = 2 * (int64_t)c->hC[d.gene] * d.Tc + 2;
+        const int shift = c->hpshift[id];
         bool changed = false;
-        for (int p = 0; p < n_pages; ++p) {
-            if (tab[p] >= 0) continue;
-            const unsigned long long need = (unsigned long long)rowlen << shift;
-            if (head + need > (unsigned long long)c->pool_cap)
-                return c->fail(DICEGP_ERR_NOMEM, "trace pool too small for the large genes of this batch; raise the trace budget");
-            tab[p] = (int64_t)head;
-            head += need;
+        for (size_t p = 0; p < tabs[i].size(); ++p) {
+            if (tabs[i][p] >= 0) continue;
+            tabs[i][p] = (int64_t)head;
+            head += (unsigned long long)rowlen << shift;
             changed = true;
         }
         if (changed)
-            DG_CUDA(c, cudaMemcpy(c->cptab.p + c->hptab_off[id], tab.data(), n_pages * sizeof(int64_t), cudaMemcpyHostToDevice));
+            DG_CUDA(c, cudaMemcpy(c->cptab.p + c->hptab_off[id], tabs[i].data(), tabs[i].size() * sizeof(int64_t), cudaMemcpyHostToDevice));
     }
     DG_CUDA(c, cudaMemcpy(c->cpool_head.p, &head, sizeof head, cudaMemcpyHostToDevice));
     return DICEGP_OK;
@@ -900,6 +912,8 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     // last stragglers (latency_mode 2): fewer chains than SMs, so every chain of the wide-round kernel gets a
     // thread-block cluster -- the largest of 8 / 4 / 2 blocks that still lets all chains run at once
     int wide_cs = 1;
+    if (latency_mode == 2 && preallocate_trace_pages(c, ids, true) != DICEGP_OK)
+        latency_mode = 1;         // no room to give every chain all its trace pages now: no clusters (pages on demand, NOMEM status)
     if (latency_mode == 2 && persistent) {
         const int n = (int)ids.size();
         const int e_cs = env_int("DICEGP_WIDE_CS", 0);
@@ -976,8 +990,10 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     const int tier_order[kTiers] = {7, 6, 5, kWideTier, 4, 3, 2, 1, 0};
     for (int to = 0; to < kTiers; ++to) {
         for (int kind_i = 0; kind_i < kKinds; ++kind_i) {
-            // straggler pass: many isoforms first (most of the chains that use all M steps are those)
-            const int kind = latency_mode ? (kind_i == kKinds - 1 ? 0 : kKinds - 1 - kind_i) : kind_i;
+            // many isoforms first: their steps are the longest, so their chains should not be the ones that start last
+            // (in the straggler pass most of the chains that use all M steps are those); DICEGP_ORDER=1: ascending in pass 0
+            static const int e_order = env_int("DICEGP_ORDER", 0);
+            const int kind = (latency_mode || e_order == 0) ? (kind_i == kKinds - 1 ? 0 : kKinds - 1 - kind_i) : kind_i;
             const int tier = tier_order[to];
             const int k = tier * kKinds + kind;
             const int n_ids = (int)by_group[k].size();
@@ -1002,7 +1018,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                     sak.delta_off = c->ddoff.p + base[k];
                     sak.u_off = c->ddoff.p + flat.size() + base[k];
                 }
-                const int wcs = wide_cs;
+                const int wcs = wide_cs;                               // (cluster passes: the pages were pre-assigned above)
                 int grid = n_ids;
                 int *queue = nullptr;
                 if (persistent) {
@@ -1013,10 +1029,6 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                 wide_kernel_t kern = wide_kernel_for(kind, wcs > 1);
                 DG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(c->smem_optin - c->static_smem_wide)));
-                if (wcs > 1) {
-                    int rc = preallocate_trace_pages(c, by_group[k]);      // only the lead block writes the trace
-                    if (rc != DICEGP_OK) return rc;
-                }
                 if (getenv("DICEGP_VERBOSE"))
                     fprintf(stderr, "[dicegp]   launch wide C-kind %d: %d chains, %d + %d warps, cluster %d, %zu B smem, grid %d\n",
                             kind == 0 ? 0 : kind + 1, n_ids, wp.ncw, wp.npw, wcs, smem, grid);
@@ -1740,9 +1752,15 @@ int dicegp_run_device_stream(dicegp_ctx *c, uint64_t seed, const int64_t *stream
     // re-launched on thread-block clusters of 2 / 4 / 8 SMs per chain (wide-round kernel, DSMEM exchange) as soon as
     // that many SMs per chain are free; once the clusters have their full size the chains run to the end.
     // DICEGP_STRAGGLER_STEPS=a[,b] fixes the plan instead (a: cap of pass 0; b: cap of a pass 1 before the cluster pass).
-    int cap0 = 4096, cap1 = 0;
+    // Cap of pass 0, measured on the time-series workload (scripts/exp_r02i.sh): with 10k chains the throughput shapes
+    // of the general kernel are as good as the wide rounds up to ~4096 steps; with few chains per SM the chains that
+    // are still running soon leave SMs half empty (a throughput shape takes 5-8 us per step, so 4096 steps of ONE
+    // chain are 20-33 ms) and the wide-round kernel (one chain per SM, 3-5 us per step) should take over early:
+    // 1250 chains 137 -> 101 ms, 2500 chains 202 -> 165 ms, 5000 chains 347 -> 323 ms.
+    int cap0 = ids.size() <= 3000 ? 1024 : (ids.size() <= 7000 ? 2048 : 4096), cap1 = 0;
     const bool fixed_plan = getenv("DICEGP_STRAGGLER_STEPS") != nullptr;
     if (const char *e = getenv("DICEGP_STRAGGLER_STEPS")) sscanf(e, "%d,%d", &cap0, &cap1);
+    if (const char *e = getenv("DICEGP_CAP0")) cap0 = atoi(e);            // cap of pass 0 only (the staged plan stays)
     if (cap0 <= 0 || max_M <= cap0) return run_chains(c, ids, max_M, sa, nullptr, true, 0);
     double ms = 0.0;
     int64_t launches = 0, evals = 0, steps = 0;
