@@ -140,7 +140,7 @@ class ClockSampler:
                 self.rows.append([str(sm), str(mx)] + ["Active" if mask & b else "Not Active" for b in bits])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(float(os.environ.get("BENCH_CLOCK_PERIOD", "0.2")))
 
     def _read(self):
         for line in self.proc.stdout:

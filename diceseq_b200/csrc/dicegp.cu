@@ -45,8 +45,15 @@ __host__ __device__ constexpr int dg_nodes_streamed(int KC) {
     return (KC >= 4 && KC <= 8) ? 4 : 3;
 #endif
 }
+// Registers: the streamed variants with a compiled isoform count run at most DG_LB_THREADS_STAGED threads per SM
+// (2-3 chains of 4-6 warps; measured shapes), which leaves them 160 registers per thread; under the 128 of a
+// 512-thread bound ptxas spilled ~300 bytes per thread into the round loop (5 % of the load instructions, long-scoreboard
+// stalls on loop counters).  The resident and run-time-C variants keep 512 threads x 128 registers.
+#ifndef DG_LB_THREADS_STAGED
+#define DG_LB_THREADS_STAGED 384
+#endif
 template <int KC, int WMODE, bool CLUSTER = false, int NJ = DG_NODES_RESIDENT>
-__global__ void __launch_bounds__(DG_LB_THREADS, 1)
+__global__ void __maxnreg__((KC > 0 && WMODE == dg::W_STAGED) ? (65536 / DG_LB_THREADS_STAGED) / 16 * 16 : (65536 / DG_LB_THREADS) / 16 * 16)   // registers are allocated in units of 16 per thread
 dicegp_chain_kernel(GeneTab gt, ChainTab ct, StreamArgs sa, const int32_t *__restrict__ ids, int n_ids,
                     int n_steps, int use_tma, int *queue) {
     extern __shared__ __align__(128) double dg_smem[];
@@ -1068,10 +1075,11 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                 // every warp of a block streams W (the state warps join the likelihood pass after the prior terms),
                 // so every warp owns a staging ring
                 int best_score = -1;
+                const int lb = kind != 0 ? DG_LB_THREADS_STAGED : DG_LB_THREADS;   // threads per SM the variant's registers allow
                 for (int kk = 1; kk <= (latency_mode ? 1 : 4); ++kk) {
-                    for (int nwl = 1; nwl <= DG_LB_THREADS / 32 - 1; ++nwl) {
+                    for (int nwl = 1; nwl <= lb / 32 - 1; ++nwl) {
                         const int thr = 32 * (maxS + nwl);
-                        if (thr * kk > DG_LB_THREADS) continue;
+                        if (thr * kk > lb) continue;
                         size_t need = fixed_smem_bytes(maxC, maxTc, thr, true) + 1024;
                         if (kind != 0) need += (size_t)ring_warps(thr, maxC, maxTc) * dg::dg_stages(maxC) * dg::dg_stage_slot_bytes(maxC);
                         if (need * kk > 233472 || need - 1024 + 127 > c->smem_optin - c->static_smem) continue;
@@ -1092,9 +1100,10 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             if (tier >= 5) {
                 // cluster tier: as many likelihood warps per block as the staging ring allows
                 int best = -1;
-                for (int nwl = 2; nwl <= DG_LB_THREADS / 32 - 2; ++nwl) {
+                const int lb = kind != 0 ? DG_LB_THREADS_STAGED : DG_LB_THREADS;
+                for (int nwl = 2; nwl <= lb / 32 - 2; ++nwl) {
                     const int thr = 32 * (maxS + nwl);
-                    if (thr > DG_LB_THREADS) break;
+                    if (thr > lb) break;
                     size_t need = fixed_smem_bytes(maxC, maxTc, thr, true, cs) + 1024;
                     if (kind != 0) need += (size_t)ring_warps(thr, maxC, maxTc) * dg::dg_stages(maxC) * dg::dg_stage_slot_bytes(maxC);
                     if (need > 233472 || need - 1024 + 127 > c->smem_optin - c->static_smem) break;
@@ -1544,10 +1553,15 @@ static int install_chains(dicegp_ctx *c, int32_t n, const dicegp_chain_desc *des
     DG_RESIZE(c->cptab_off, n); DG_RESIZE(c->cpshift, n); DG_RESIZE(c->cptab, ptab.size()); DG_RESIZE(c->cpool_head, 1);
     {
         // trace pool: first pages + room for growth, bounded by the budget
-        size_t free_b = 0, total_b = 0;
-        DG_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
-        free_b += c->ctrace.n * sizeof(double);                      // the old pool is reused / replaced
-        int64_t budget = c->trace_budget_bytes > 0 ? c->trace_budget_bytes : (int64_t)(free_b * 0.6);
+        // (cudaMemGetInfo goes through the resource manager and was seen to take tens of ms now and then on a box
+        // whose GPUs are being monitored: only asked when no budget was set)
+        int64_t budget = c->trace_budget_bytes;
+        if (budget <= 0) {
+            size_t free_b = 0, total_b = 0;
+            DG_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+            free_b += c->ctrace.n * sizeof(double);                  // the old pool is reused / replaced
+            budget = (int64_t)(free_b * 0.6);
+        }
         int64_t cap = std::min<int64_t>(worst, std::max<int64_t>(budget / 8, tr));
         if (c->ctrace.resize(cap) != cudaSuccess) {
             char msg[200];
@@ -1952,7 +1966,10 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
         scr_sorted[i] = scr_total;
         scr_total += (int64_t)keep * ((int64_t)c->hC[d.gene] * d.Tc + 1);
     }
-    if (c->skeys.resize((size_t)std::max<int64_t>(scr_total, 1)) != cudaSuccess || c->sscr_off.resize(n) != cudaSuccess)
+    // (grown with 25 % headroom: the kept rows differ from batch to batch by a few per cent, and a cudaFree + cudaMalloc of
+    // several GB inside a step costs more than the summary kernels)
+    if (((size_t)scr_total > c->skeys.n && c->skeys.resize((size_t)(scr_total + scr_total / 4 + 1)) != cudaSuccess) ||
+        c->sscr_off.resize(n) != cudaSuccess)
         return c->fail(DICEGP_ERR_NOMEM, "posterior_summary: device allocation failed (transposed trace scratch)");
     DevBuf<double> &dmean = c->smean, &dci = c->sci, &dlik = c->slik;
     DevBuf<int64_t> &doff = c->soff;
