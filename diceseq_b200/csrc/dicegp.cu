@@ -730,15 +730,15 @@ int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain, int
 struct WidePlan { int ncw, npw, bps, rj; };
 inline int env_int(const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; }
 WidePlan wide_plan(int C, int cs = 1) {
-    // One block per SM.  16 consumer warps + 2 producer warps for a whole chain (the stream of the ~13 steps a
-    // round commits costs one warp ~55k cycles, about as long as the likelihood pass of a C = 8 chain); on a
-    // cluster the likelihood pass shrinks with the cluster size while the stream does not: 12 consumers + 6
+    // One block of 16 warps per SM.  15 consumer warps + 1 producer warp for a whole chain (the stream of the ~13 steps
+    // a round commits costs one warp ~55k cycles, a little less than the likelihood pass of a C = 8 chain); on a
+    // cluster the likelihood pass shrinks with the cluster size while the stream does not: 11 consumers + 5
     // producers.  DICEGP_WIDE_NCW / _NPW / _BPS override.
     static const int e_ncw = env_int("DICEGP_WIDE_NCW", 0), e_bps = env_int("DICEGP_WIDE_BPS", 0), e_npw = env_int("DICEGP_WIDE_NPW", 0);
     WidePlan p;
     p.rj = 4;
     (void)C;
-    p.ncw = cs > 1 ? 12 : 16; p.npw = cs > 1 ? 6 : 2; p.bps = 1;
+    p.ncw = cs > 1 ? 11 : 15; p.npw = cs > 1 ? 5 : 1; p.bps = 1;
     if (e_ncw > 0) p.ncw = e_ncw;
     if (e_npw > 0) p.npw = e_npw;
     if (32 * (p.ncw + p.npw) > DG_WIDE_THREADS) p.ncw = DG_WIDE_THREADS / 32 - p.npw;

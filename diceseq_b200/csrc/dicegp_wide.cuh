@@ -47,7 +47,10 @@
 
 #define DG_WIDE_SLOTS 8             // ring slots (tasks in flight) per consumer warp
 #define DG_WIDE_MAXCT 128           // latent values (C * Tc) of a chain this kernel takes
-#define DG_WIDE_THREADS 576         // launch bound: 17 warps (16 consumers + aux) or 2 blocks of 9 warps per SM
+#ifndef DG_WIDE_THREADS
+#define DG_WIDE_THREADS 512         // launch bound: 16 warps x 128 registers (registers come in units of 16 per thread: 17-18
+                                    // warps would get 96 and spill into the task loop; measured 98 -> 90 ms on the straggler pass)
+#endif
 #define DG_WIDE_MAXCS 8             // blocks of a thread-block cluster that share one chain
 
 #ifdef DG_PROFILE
