@@ -386,15 +386,20 @@ __device__ void dg_radix_select2(const unsigned long long *keys, int n, int rank
 __global__ void __launch_bounds__(DG_SUM_THREADS)
 dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, double *__restrict__ mean_out,
                       double *__restrict__ ci_out, const int64_t *__restrict__ out_off, double *__restrict__ lik_out,
-                      double *__restrict__ scratch, const int64_t *__restrict__ scr_off, int keys_in_smem) {
+                      double *__restrict__ scratch, const int64_t *__restrict__ scr_off, int keys_in_smem, int parts) {
     extern __shared__ __align__(16) unsigned long long dg_keys_smem[];
     // phase 1 uses the dynamic shared memory as a 32 x 65 tile, phase 2 as one column of keys
     double (*tile)[DG_SUM_TILE_COLS + 1] = reinterpret_cast<double (*)[DG_SUM_TILE_COLS + 1]>(dg_keys_smem);
     __shared__ unsigned hist[512];
     __shared__ int sh[4];
     __shared__ double red[DG_SUM_THREADS / 32];
-    const int chain = ids[blockIdx.x];
+    // `parts` blocks share one chain (the long chains: a 20000-step chain is 15000 rows x CT columns of radix
+    // selects, 9 ms in one block): block `part` owns the columns [c_lo, c_hi); the last one also the log-likelihood
+    const int slot = blockIdx.x / parts, part = blockIdx.x - slot * parts;
+    const int chain = ids[slot];
     const int C = gt.C[ct.gene[chain]], Tc = ct.Tc[chain], CT = C * Tc, rowlen = 2 * CT + 2;
+    const int c_lo = (int)((long long)part * CT / parts), c_hi = (int)((long long)(part + 1) * CT / parts);
+    const bool owns_lik = part == parts - 1;
     const int state = ct.state[chain], m_ret = ct.m_ret[chain];
     const int n_rows = state == dg::DICEGP_CHAIN_CONVERGED_ ? m_ret
                        : (state == dg::DICEGP_CHAIN_EXHAUSTED_ ? ct.M[chain] : ct.m_next[chain]);
@@ -402,19 +407,19 @@ dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, 
     const int n = n_rows - b;
     TraceView tv;
     tv.pool = ct.trace; tv.tab = ct.ptab + ct.ptab_off[chain]; tv.shift = ct.pshift[chain]; tv.rowlen = rowlen;
-    double *mean = mean_out + out_off[blockIdx.x];
-    double *ci = ci_out + 2 * out_off[blockIdx.x];
+    double *mean = mean_out + out_off[slot];
+    double *ci = ci_out + 2 * out_off[slot];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (n <= 0) {
-        for (int i = tid; i < CT; i += blockDim.x) { mean[i] = nan(""); ci[2 * i] = nan(""); ci[2 * i + 1] = nan(""); }
-        if (tid == 0) lik_out[blockIdx.x] = nan("");
+        for (int i = c_lo + tid; i < c_hi; i += blockDim.x) { mean[i] = nan(""); ci[2 * i] = nan(""); ci[2 * i + 1] = nan(""); }
+        if (tid == 0 && owns_lik) lik_out[slot] = nan("");
         return;
     }
-    double *cols = scratch + scr_off[blockIdx.x];                 // (CT + 1) columns of n doubles
+    double *cols = scratch + scr_off[slot];                       // (CT + 1) columns of n doubles
     // ---- phase 1: means (rows in order, like numpy's axis-0 reduction) + transposed copy ----
-    for (int c0 = 0; c0 < CT; c0 += DG_SUM_TILE_COLS) {
-        const int w = min(DG_SUM_TILE_COLS, CT - c0);
-        const bool last = c0 + w == CT;
+    for (int c0 = c_lo; c0 < c_hi; c0 += DG_SUM_TILE_COLS) {
+        const int w = min(DG_SUM_TILE_COLS, c_hi - c0);
+        const bool last = owns_lik && c0 + w == CT;
         const int wl = w + (last && w < DG_SUM_TILE_COLS ? 1 : 0);   // the log-likelihood column rides along when there is room
         double a = 0.0;
         for (int r0 = 0; r0 < n; r0 += 32) {
@@ -439,7 +444,7 @@ dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, 
     __syncthreads();
     // ---- phase 2: per column radix select of ranks k and n-k (k = 0 -> both the minimum side quirk) ----
     const int k = (int)((double)n * (1.0 - 0.95) / 2.0);
-    for (int col = 0; col < CT; ++col) {
+    for (int col = c_lo; col < c_hi; ++col) {
         const unsigned long long *src = reinterpret_cast<const unsigned long long *>(cols + (size_t)col * n);
         const unsigned long long *keys = src;                     // long chains select in the scratch itself
         if (keys_in_smem) {
@@ -456,6 +461,11 @@ dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, 
         }
     }
     // harmonic-mean log-likelihood
+    if (!owns_lik) return;
+    if (c_lo == c_hi) {                                           // more parts than columns: this block copied nothing yet
+        for (int i = tid; i < n; i += DG_SUM_THREADS) cols[(size_t)CT * n + i] = __ldcg(tv.row(b + i) + 2 * CT + 1);
+        __syncthreads();
+    }
     const double *lk = cols + (size_t)CT * n;
     double mn = INFINITY;
     for (int i = tid; i < n; i += blockDim.x) mn = fmin(mn, __ldcg(lk + i));
@@ -474,7 +484,7 @@ dicegp_summary_kernel(GeneTab gt, ChainTab ct, const int32_t *__restrict__ ids, 
     if (tid == 0) {
         double t = 0.0;
         for (int w = 0; w < DG_SUM_THREADS / 32; ++w) t += red[w];
-        lik_out[blockIdx.x] = log((double)n) + mn - log(t);
+        lik_out[slot] = log((double)n) + mn - log(t);
     }
 }
 
@@ -1998,9 +2008,12 @@ int dicegp_posterior_summary(dicegp_ctx *c, int32_t n, const int32_t *chain_ids,
                                                32 * (DG_SUM_TILE_COLS + 1) * sizeof(double));
             cudaStream_t st = c->class_stream[k];
             if ((e = cudaStreamWaitEvent(st, c->ev_fork, 0)) != cudaSuccess) break;
-            dicegp_summary_kernel<<<cnt, DG_SUM_THREADS, sm, st>>>(make_gene_tab(c), make_chain_tab(c), dids.p + gstart[k],
-                                                                   dmean.p, dci.p, doff.p + gstart[k], dlik.p + gstart[k],
-                                                                   reinterpret_cast<double *>(c->skeys.p), c->sscr_off.p + gstart[k], k == 4 ? 0 : 1);
+            // the long classes are few chains of many rows: eight blocks per chain, each a share of the columns
+            const int parts = k >= 2 ? 8 : 1;
+            dicegp_summary_kernel<<<cnt * parts, DG_SUM_THREADS, sm, st>>>(make_gene_tab(c), make_chain_tab(c), dids.p + gstart[k],
+                                                                           dmean.p, dci.p, doff.p + gstart[k], dlik.p + gstart[k],
+                                                                           reinterpret_cast<double *>(c->skeys.p), c->sscr_off.p + gstart[k],
+                                                                           k == 4 ? 0 : 1, parts);
             ++c->total_launches;
             if ((e = cudaGetLastError()) != cudaSuccess) break;
             if ((e = cudaEventRecord(c->ev_join[k], st)) != cudaSuccess) break;
