@@ -120,6 +120,22 @@ def test_device_summary_matches_numpy(sampler):
         assert abs(r.lik_marg - lik_marg) <= 1e-13 * abs(lik_marg)
 
 
+def test_summary_of_long_chains_split_over_blocks(sampler):
+    """Chains of 7k-28k rows take the size classes that run eight blocks per chain (each a share of the
+    columns, the last one the log-likelihood too): same bit-exact summaries."""
+    genes = [95, 96]
+    packed = _batch("timeseries", genes, reads=80, T=3)
+    res = sampler.run(packed, M=9000, initial=9000, gap=1000, seed=5, gene_ids=genes, keep_trace=True)
+    for r in res:
+        Psi, Y, Pro, Lik = r.trace
+        assert len(Lik) == 9000
+        psi_mean, psi_95, lik_marg, _ = orc.posterior_summary(Psi, Y, Lik, r.m)
+        assert np.array_equal(r.psi_mean, psi_mean)
+        for c in range(Psi.shape[1]):
+            assert np.array_equal(r.psi_95[c], psi_95[c])
+        assert abs(r.lik_marg - lik_marg) <= 1e-13 * abs(lik_marg)
+
+
 def test_summary_of_chains_longer_than_shared_memory():
     """`--mcmc 0 50000 ...`: a chain that keeps more rows after the burn-in than one column of keys fits
     shared memory (about 28.5k) is summarised through a global scratch row: same bit-exact mean /
