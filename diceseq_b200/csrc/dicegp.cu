@@ -651,7 +651,6 @@ ChainTab make_chain_tab(dicegp_ctx *c) {
     t.trace = c->ctrace.p; t.st = c->cst.p; t.m_next = c->cm_next.p; t.cnt = c->ccnt.p;
     t.state = c->cstate.p; t.m_ret = c->cm_ret.p; t.flags = c->cflags.p;
     t.ctr = c->dctr.p;
-    t.l2pin = 0;
     return t;
 }
 
@@ -1008,9 +1007,9 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     for (int to = 0; to < kTiers; ++to) {
         for (int kind_i = 0; kind_i < kKinds; ++kind_i) {
             // many isoforms first: their steps are the longest, so their chains should not be the ones that start last
-            // (in the straggler pass most of the chains that use all M steps are those); DICEGP_ORDER=1: ascending in pass 0
-            static const int e_order = env_int("DICEGP_ORDER", 0);
-            const int kind = (latency_mode || e_order == 0) ? (kind_i == kKinds - 1 ? 0 : kKinds - 1 - kind_i) : kind_i;
+            // (in the straggler pass most of the chains that use all M steps are those; in pass 0 the order was
+            // measured to make no difference)
+            const int kind = kind_i == kKinds - 1 ? 0 : kKinds - 1 - kind_i;
             const int tier = tier_order[to];
             const int k = tier * kKinds + kind;
             const int n_ids = (int)by_group[k].size();
@@ -1171,15 +1170,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                 attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
                 cfg.attrs = attr; cfg.numAttrs = 1;
                 const int32_t *ids_arg = c->dids.p + base[k];
-                ChainTab ctk = ct;
-                if (tier == 4 && kind != 0) {
-                    // development knob: DICEGP_L2_PIN = "p2,p3,...,p8", sixteenths of W kept in L2 per isoform count
-                    int pins[9] = {0};
-                    if (const char *e = getenv("DICEGP_L2_PIN"))
-                        sscanf(e, "%d,%d,%d,%d,%d,%d,%d", &pins[2], &pins[3], &pins[4], &pins[5], &pins[6], &pins[7], &pins[8]);
-                    ctk.l2pin = pins[kind + 1];
-                }
-                cudaError_t e = cudaLaunchKernelEx(&cfg, kern, gt, ctk, sak, ids_arg, n_ids, n_steps, c->use_tma, queue);
+                cudaError_t e = cudaLaunchKernelEx(&cfg, kern, gt, ct, sak, ids_arg, n_ids, n_steps, c->use_tma, queue);
                 if (e == cudaSuccess) e = cudaGetLastError();
                 if (e != cudaSuccess) return c->cuda_fail(e, "chain kernel launch");
             }

@@ -94,22 +94,6 @@ __host__ __device__ constexpr int dg_stages(int C) {
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dg_smem_u32(dst_smem)), "l"(src) : "memory");
 }
-// the same copy with an L2 eviction policy (createpolicy): part of every chain's W is kept in L2 with
-// evict_last while the rest streams through with evict_first, so that a working set larger than L2 does
-// not thrash it (a cyclic sweep over more bytes than the cache holds hits nothing under LRU)
-__device__ __forceinline__ void cp_async16_hint(void *dst_smem, const void *src, uint64_t pol) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dg_smem_u32(dst_smem)), "l"(src), "l"(pol) : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy_keep() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_stream() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -132,7 +116,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int KC, int J, int WMODE, bool LOGPATH>
 __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, int Tc, const int *rel, const int *ncnt,
                                          const int *cum, const double *ff, double *stage, int lane, int q0, int q1,
-                                         int &ring_pos, int pin16, double (&mm)[J], int (&ee)[J], unsigned &bad, double (&ls)[J]) {
+                                         int &ring_pos, double (&mm)[J], int (&ee)[J], unsigned &bad, double (&ls)[J]) {
     constexpr int JP = (J + 1) & ~1;
     constexpr int IW = dg_item_words(KC > 0 ? KC : DG_MAXC), IP = 32 * IW;   // 16-byte words per lane, read pairs per item
     constexpr int kStages = dg_stages(KC > 0 ? KC : DG_MAXC);
@@ -150,24 +134,12 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
             ip = (qi - cum[ti]) * IP + lane;
             isrc = reinterpret_cast<const double2 *>(Wc + (size_t)C * r0) + ip;
         }
-        if (pin16 > 0) {                                                 // uniform: the first pin16/16 of the run stay in L2
-            const uint64_t pol = ((qi - q0) * 16 < pin16 * (q1 - q0)) ? l2_policy_keep() : l2_policy_stream();
 #pragma unroll
-            for (int w = 0; w < IW; ++w) {
-                if (ip + 32 * w < inp) {
+        for (int w = 0; w < IW; ++w) {
+            if (ip + 32 * w < inp) {
 #pragma unroll
-                    for (int k = 0; k < kmax; ++k)
-                        cp_async16_hint(mystage + ((slot * kmax + k) * IW + w) * 32, isrc + 32 * w + (size_t)k * inp, pol);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int w = 0; w < IW; ++w) {
-                if (ip + 32 * w < inp) {
-#pragma unroll
-                    for (int k = 0; k < kmax; ++k)
-                        cp_async16(mystage + ((slot * kmax + k) * IW + w) * 32, isrc + 32 * w + (size_t)k * inp);
-                }
+                for (int k = 0; k < kmax; ++k)
+                    cp_async16(mystage + ((slot * kmax + k) * IW + w) * 32, isrc + 32 * w + (size_t)k * inp);
             }
         }
         ++qi; ip += IP; isrc += IP;
@@ -307,13 +279,13 @@ __device__ __forceinline__ void lik_pass(const double *__restrict__ Wc, int C, i
 template <int KC, int J, int WMODE>
 __device__ __noinline__ void lik_warp_pass_log(const double *Wc, const int *rel, const int *ncnt, const int *cum,
                                                const double *ff, double *stage, double *red, int C, int Tc, int q0, int q1,
-                                               int &ring_pos, int pin16, int lane, int wl, int slots, int cs) {
+                                               int &ring_pos, int lane, int wl, int slots, int cs) {
     double mm[J], ls[J];
     int ee[J];
     unsigned bad = 0u;
 #pragma unroll
     for (int j = 0; j < J; ++j) { mm[j] = 1.0; ls[j] = 0.0; ee[j] = 0; }
-    lik_pass<KC, J, WMODE, true>(Wc, C, Tc, rel, ncnt, cum, ff, stage, lane, q0, q1, ring_pos, pin16, mm, ee, bad, ls);
+    lik_pass<KC, J, WMODE, true>(Wc, C, Tc, rel, ncnt, cum, ff, stage, lane, q0, q1, ring_pos, mm, ee, bad, ls);
 #pragma unroll
     for (int j = 0; j < J; ++j) {
         double v = ls[j];
@@ -883,7 +855,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             unsigned bad = 0u;
 #pragma unroll
             for (int j = 0; j < J; ++j) { mm[j] = 1.0; ee[j] = 0; lsd[j] = 0.0; }
-            lik_pass<KC, J, WMODE, false>(Wc, C, Tc, rel, ncnt, cum, ff, stage, lane, lq0, lq1, ring_pos, ct.l2pin, mm, ee, bad, lsd);
+            lik_pass<KC, J, WMODE, false>(Wc, C, Tc, rel, ncnt, cum, ff, stage, lane, lq0, lq1, ring_pos, mm, ee, bad, lsd);
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const int gg = __double2hiint(mm[j]);
@@ -1026,7 +998,7 @@ __device__ void run_chain(const GeneTab &gt, const ChainTab &ct, const StreamArg
             if (cs > 1) xbuf ^= 1;
             if (redo) {                                                      // rare: some x_n was not a positive normal
                 lik_warp_pass_log<KC, J, WMODE>(Wc, rel, ncnt, cum, ff, stage, red + xbuf * J * SLOTS, C, Tc, lq0, lq1,
-                                                ring_pos, ct.l2pin, lane, gwl, SLOTS, cs);
+                                                ring_pos, lane, gwl, SLOTS, cs);
                 if (cs == 1) __syncthreads(); else cluster_barrier();
             }
         } while (redo);

@@ -64,9 +64,6 @@ struct ChainTab {
     // [1] rounds (passes over W), [2] candidate evaluations (rounds x candidates x reads), [3] steps,
     // [4] fp64 fused multiply-adds of those evaluations (x isoforms)
     unsigned long long *ctr;
-    // streamed tiers: sixteenths of every warp's run of W that are copied with the L2 evict_last policy (the rest
-    // with evict_first); 0 = plain copies
-    int32_t l2pin;
 };
 
 struct StreamArgs {
