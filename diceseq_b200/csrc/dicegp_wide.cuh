@@ -18,9 +18,9 @@
 //   LIK    reads in TASKS of 16 words (32 reads) of one time point.  W is read from a TILED copy (GeneTab::Wt,
 //          made on the device after the upload): a tile = the C rows of one task back to back, tiles in
 //          (time, position) order, so the contiguous run of tasks a warp owns is ONE byte range.  Each consumer
-//          warp streams its run through its OWN ring of up to 8 slots with 1-D TMA bulk copies
+//          warp streams its run through its OWN ring of two-task slots with 1-D TMA bulk copies
 //          (cp.async.bulk + mbarrier complete_tx, one copy per slot, issued by lane 0 when the slot has been
-//          consumed); the sequence repeats every round, so the first slots of the next round are in flight
+//          consumed; the ring cursor is kept in running counters, no divisions); the sequence repeats every round, so the first slots of the next round are in flight
 //          while this round decides; a run that fits the ring is loaded once (W resident).  No block-level
 //          synchronisation inside the pass.
 //          Lane (s, h), s = lane & 7, h = lane >> 3: words s and s + 8 of the task (4 reads), candidates
@@ -36,12 +36,12 @@
 // Five block barriers per round.  Same stream, same saved state, same paged trace and incremental Geweke
 // sums as dg::run_chain -- a chain can be advanced by either kernel in turn.
 //
-// Measured (profiles/): per round at C = 8, 16 consumer warps: S 12k, likelihood 70-80k (the tile
-// loop reaches 39 of 64 DFMA lane-ops per clock in isolation, scripts/ubench/lik_tile.cu; in the kernel the
-// barrier waits, copy issue and per-task bookkeeping halve that), decide + update 12k cycles, for ~12 steps at
-// the acceptance rates of the straggler pass.  Used there (one chain per SM, W L2 resident): 20 % faster than
-// the general kernel.  In the throughput pass the general kernel's 2-4 chains per SM at 4 candidates per
-// round spend a third less fp64 work per committed step and win.
+// Measured (profiles/): per round at C = 8, 15 consumer warps + 1 producer at 128 registers: S 8k,
+// likelihood 48k (tasks 38k: the tile loop is bound by the shared-memory and fp64 pipes together), decide + update 5k,
+// rows 3k cycles for ~13 steps at the acceptance rates of the straggler pass = 2.7 us per step.  Used for the straggler
+// pass (one chain per SM, W L2 resident) and, with few chains per SM, from step 1024 on; in the throughput pass of a full
+// batch the general kernel's 2-3 chains per SM at 4 candidates per round spend a third less fp64 work per committed
+// step and win.
 #pragma once
 #include "dicegp_chain.cuh"
 
