@@ -270,6 +270,19 @@ def test_last_stragglers_on_clusters_step_parity(ctx, monkeypatch, cs):
     check_main(out, inputs, 1250, 1000, 50)
 
 
+def test_cluster_passes_with_a_minus_inf_gene(ctx, monkeypatch):
+    """The real-log redo path on a cluster: a gene whose likelihood is -inf makes every
+    round exchange its partial sums twice through DSMEM; the chain never moves and stops at the first check,
+    the ordinary gene beside it keeps step parity."""
+    monkeypatch.setenv("DICEGP_STRAGGLER_STEPS", "150,250")
+    monkeypatch.setenv("DICEGP_WIDE_CS", "4")
+    genes = [550, 551]
+    inputs = [zero_row_gene(3, 3), synth.gene_matrices("timeseries", 551, reads=200, T=3, C=4)]
+    out = run_pipeline(ctx, inputs, genes, seed=53, M=1150, initial=1000, gap=50)
+    check_main(out, inputs, 1150, 1000, 50)
+    assert int(out["st"]["cnt"][0]) == 0
+
+
 def test_cluster_tier_device_stream_step_parity(ctx):
     """A gene whose W (1.3 MB) takes the thread-block-cluster tier, device-stream mode."""
     genes = [530]
