@@ -120,6 +120,24 @@ def test_device_summary_matches_numpy(sampler):
         assert abs(r.lik_marg - lik_marg) <= 1e-13 * abs(lik_marg)
 
 
+def test_results_do_not_depend_on_the_pass_plan(sampler, monkeypatch):
+    """Which kernel advances a chain and where the passes are cut must not show in the results: same counter-based
+    stream, same arithmetic per step.  Default plan (small batch: general kernel to step 1024, then wide rounds)
+    against general kernel to 4096 + staged cluster passes, and against a very early hand-over."""
+    genes = list(range(700, 760))
+    packed = _batch("timeseries", genes, reads=150, T=4)
+    ref = sampler.run(packed, seed=17, gene_ids=genes)
+    for env in ({"DICEGP_CAP0": "4096"}, {"DICEGP_CAP0": "4096", "DICEGP_WIDE_CS": "2"}, {"DICEGP_CAP0": "200"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got = sampler.run(packed, seed=17, gene_ids=genes)
+        for k in env:
+            monkeypatch.delenv(k)
+        assert np.array_equal(got.m, ref.m) and np.array_equal(got.cnt, ref.cnt), env
+        assert np.array_equal(got.psi_mean, ref.psi_mean), env
+        assert np.all(np.abs(got.lik_marg - ref.lik_marg) <= 1e-12 * np.abs(ref.lik_marg)), env
+
+
 def test_summary_of_long_chains_split_over_blocks(sampler):
     """Chains of 7k-28k rows take the size classes that run eight blocks per chain (each a share of the
     columns, the last one the log-likelihood too): same bit-exact summaries."""
