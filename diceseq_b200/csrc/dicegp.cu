@@ -657,7 +657,9 @@ ChainTab make_chain_tab(dicegp_ctx *c) {
 // Residency tiers: W resident in shared memory at 8/4/2/1 blocks per SM, then the tier
 // that streams W from L2/HBM every step.  Each tier is further split by isoform count,
 // because the likelihood loop is compiled per C (weights f[C] in registers).
-constexpr int kTiers = 9;                     // 0-3 resident, 4 streamed, 5-7 streamed over a cluster of 2/4/8 blocks, 8 wide rounds (dicegp_wide.cuh)
+// 0-3 resident, 4 streamed, 5-7 streamed over a cluster of 2/4/8 blocks; wide rounds (dicegp_wide.cuh): 8 = one block per
+// chain (or the cluster size of a last-stragglers pass), 9-11 = large genes on a cluster of 2/4/8 blocks in the straggler passes
+constexpr int kTiers = 12;
 constexpr int kWideTier = 8;
 constexpr int kKinds = 8;                      // kernel variants by C: generic, 2..8
 constexpr int kGroups = kTiers * kKinds;
@@ -738,30 +740,31 @@ int pick_tier(const dicegp_ctx *c, const LaunchClass cls[kTiers], int chain, int
 // ---- wide-round kernel (dicegp_wide.cuh): launch shape per isoform count ----------------------
 struct WidePlan { int ncw, npw, bps, rj; };
 inline int env_int(const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; }
-WidePlan wide_plan(int C, int cs = 1) {
-    // One block of 16 warps per SM.  15 consumer warps + 1 producer warp for a whole chain (the stream of the ~13 steps
-    // a round commits costs one warp ~55k cycles, a little less than the likelihood pass of a C = 8 chain); on a
-    // cluster the likelihood pass shrinks with the cluster size while the stream does not: 11 consumers + 5
-    // producers.  DICEGP_WIDE_NCW / _NPW / _BPS override.
-    static const int e_ncw = env_int("DICEGP_WIDE_NCW", 0), e_bps = env_int("DICEGP_WIDE_BPS", 0), e_npw = env_int("DICEGP_WIDE_NPW", 0);
-    WidePlan p;
-    p.rj = 4;
-    (void)C;
-    p.ncw = cs > 1 ? 11 : 15; p.npw = cs > 1 ? 5 : 1; p.bps = 1;
-    if (e_ncw > 0) p.ncw = e_ncw;
-    if (e_npw > 0) p.npw = e_npw;
-    if (32 * (p.ncw + p.npw) > DG_WIDE_THREADS) p.ncw = DG_WIDE_THREADS / 32 - p.npw;
-    if (e_bps > 0) p.bps = e_bps;
-    if (32 * (p.ncw + p.npw) * p.bps > DG_WIDE_THREADS) p.bps = std::max(1, DG_WIDE_THREADS / (32 * (p.ncw + p.npw)));
-    return p;
-}
 inline size_t wide_fixed_bytes(int C, int Tc, const WidePlan &p) {
     return (size_t)dg::dg_wide_layout(C, Tc, p.ncw, 4 * p.rj, p.npw).ring * sizeof(double);
 }
 inline size_t wide_budget(const dicegp_ctx *c, const WidePlan &p) {
     return std::min<size_t>(233472 / p.bps - 1024, c->smem_optin - c->static_smem_wide);
 }
-bool wide_eligible(const dicegp_ctx *c, int chain, int latency_mode) {
+WidePlan wide_plan(const dicegp_ctx *c, int C, int Tc, int cs = 1) {
+    // One block of 16 warps per SM.  15 consumer warps + 1 producer warp for a whole chain (the stream of the ~13 steps
+    // a round commits costs one warp ~55k cycles, a little less than the likelihood pass of a C = 8 chain); on a
+    // cluster the likelihood pass shrinks with the cluster size while the stream does not: 11 consumers + 5
+    // producers.  Every consumer warp needs two tasks (C x 256 bytes each) of ring: genes with many isoforms get
+    // fewer consumer warps.  DICEGP_WIDE_NCW / _NPW / _BPS override.
+    static const int e_ncw = env_int("DICEGP_WIDE_NCW", 0), e_bps = env_int("DICEGP_WIDE_BPS", 0), e_npw = env_int("DICEGP_WIDE_NPW", 0);
+    WidePlan p;
+    p.rj = 4;
+    p.ncw = cs > 1 ? 11 : 15; p.npw = cs > 1 ? 5 : 1; p.bps = 1;
+    if (e_ncw > 0) p.ncw = e_ncw;
+    if (e_npw > 0) p.npw = e_npw;
+    if (32 * (p.ncw + p.npw) > DG_WIDE_THREADS) p.ncw = DG_WIDE_THREADS / 32 - p.npw;
+    if (e_bps > 0) p.bps = e_bps;
+    if (32 * (p.ncw + p.npw) * p.bps > DG_WIDE_THREADS) p.bps = std::max(1, DG_WIDE_THREADS / (32 * (p.ncw + p.npw)));
+    while (p.ncw > 4 && wide_fixed_bytes(C, Tc, p) + 2 * (size_t)p.ncw * C * 256 > wide_budget(c, p)) --p.ncw;
+    return p;
+}
+bool wide_eligible(const dicegp_ctx *c, int chain, int latency_mode, int cs = 1) {
     // DICEGP_WIDE: 0 never, 1 (default) the straggler pass only, 2 every pass.  In the throughput pass two to
     // four chains of the general kernel per SM overlap each other's serial parts and spend a third less fp64
     // work per committed step (4 candidates per round instead of 16); with one chain per SM, W L2 resident
@@ -771,7 +774,7 @@ bool wide_eligible(const dicegp_ctx *c, int chain, int latency_mode) {
     const dicegp_chain_desc &d = c->hdesc[chain];
     const int C = c->hC[d.gene];
     if (C < 2 || C * d.Tc > DG_WIDE_MAXCT) return false;
-    const WidePlan p = wide_plan(C);
+    const WidePlan p = wide_plan(c, C, d.Tc, cs);
     const size_t stage = (size_t)p.ncw * C * 256;
     return wide_fixed_bytes(C, d.Tc, p) + 2 * stage <= wide_budget(c, p);
 }
@@ -936,18 +939,21 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
         wide_cs = n <= wide_cluster_capacity(c, 8) ? 8 : (n <= wide_cluster_capacity(c, 4) ? 4 : (n <= wide_cluster_capacity(c, 2) ? 2 : 1));
         if (e_cs == 1 || e_cs == 2 || e_cs == 4 || e_cs == 8) wide_cs = e_cs;
     }
+    static const int wide_big = env_int("DICEGP_WIDE_BIG", 1);
     for (size_t i = 0; i < ids.size(); ++i) {
         const dicegp_chain_desc &d = c->hdesc[ids[i]];
         const int C = c->hC[d.gene];
         int tier = pick_tier(c, cls, ids[i], latency_mode);
         if (tier <= 4 && wide_eligible(c, ids[i], latency_mode)) tier = kWideTier;   // wide rejection-chain rounds
+        else if (latency_mode && persistent && tier >= 5 && tier <= 7 && wide_big && wide_eligible(c, ids[i], latency_mode, tier_cluster(tier)))
+            tier = kWideTier + 1 + (tier - 5);                 // large genes: the same rounds on a cluster of 2 / 4 / 8 blocks
         if (latency_mode == 2 && tier == 4) tier = 6;          // last stragglers: a cluster of 4 blocks each
         const int k = tier * kKinds + kind_of(C);
         by_group[k].push_back(ids[i]);
         slot_src[k].push_back((int32_t)i);
     }
-    for (int kind = 0; kind < kKinds; ++kind)
-        if (!by_group[kWideTier * kKinds + kind].empty()) {
+    for (int k = kWideTier * kKinds; k < kGroups; ++k)
+        if (!by_group[k].empty()) {
             int rc = ensure_tiles(c);
             if (rc != DICEGP_OK) return rc;
             break;
@@ -1003,7 +1009,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     int64_t launches = 0;
     int next_stream = 0;
     // big tiers first: the 1-block-per-SM and streaming launches carry most of the work
-    const int tier_order[kTiers] = {7, 6, 5, kWideTier, 4, 3, 2, 1, 0};
+    const int tier_order[kTiers] = {7, 6, 5, kWideTier + 3, kWideTier + 2, kWideTier + 1, kWideTier, 4, 3, 2, 1, 0};
     for (int to = 0; to < kTiers; ++to) {
         for (int kind_i = 0; kind_i < kKinds; ++kind_i) {
             // many isoforms first: their steps are the longest, so their chains should not be the ones that start last
@@ -1014,10 +1020,19 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             const int k = tier * kKinds + kind;
             const int n_ids = (int)by_group[k].size();
             if (n_ids == 0) continue;
-            if (tier == kWideTier) {
-                int maxC = 2;
-                for (int32_t id : by_group[k]) maxC = std::max(maxC, c->hC[c->hdesc[id].gene]);
-                const WidePlan wp = wide_plan(kind == 0 ? maxC : kind + 1, wide_cs);
+            if (tier >= kWideTier) {
+                int maxC = 2, maxTcw = 1;
+                for (int32_t id : by_group[k]) {
+                    maxC = std::max(maxC, c->hC[c->hdesc[id].gene]);
+                    maxTcw = std::max(maxTcw, c->hdesc[id].Tc);
+                }
+                // cluster size: that of the pass (last stragglers), or the large gene's own tier
+                const int wcs = tier == kWideTier ? wide_cs : (2 << (tier - kWideTier - 1));
+                const WidePlan wp = wide_plan(c, kind == 0 ? maxC : kind + 1, maxTcw, wcs);
+                if (tier > kWideTier) {
+                    int rc = preallocate_trace_pages(c, by_group[k]);     // only the lead block writes the trace
+                    if (rc != DICEGP_OK) return rc;
+                }
                 size_t fixed = 0;
                 for (int32_t id : by_group[k]) {
                     const dicegp_chain_desc &d = c->hdesc[id];
@@ -1034,8 +1049,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                     sak.delta_off = c->ddoff.p + base[k];
                     sak.u_off = c->ddoff.p + flat.size() + base[k];
                 }
-                const int wcs = wide_cs;                               // (cluster passes: the pages were pre-assigned above)
-                int grid = n_ids;
+                int grid = n_ids;                                      // (last-stragglers passes: the pages were pre-assigned above)
                 int *queue = nullptr;
                 if (persistent) {
                     grid = std::min(n_ids, wcs > 1 ? wide_cluster_capacity(c, wcs) : c->sm_count * wp.bps);

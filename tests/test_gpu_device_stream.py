@@ -283,6 +283,17 @@ def test_cluster_passes_with_a_minus_inf_gene(ctx, monkeypatch):
     assert int(out["st"]["cnt"][0]) == 0
 
 
+def test_large_genes_on_wide_cluster_rounds_step_parity(ctx, monkeypatch):
+    """Straggler passes of large genes (W >= 1 MB: the cluster tiers): 16-candidate rounds on a cluster of 2 blocks
+    (wide-round kernel, compiled and run-time isoform counts) after a first pass of the general cluster kernel."""
+    monkeypatch.setenv("DICEGP_STRAGGLER_STEPS", "120")
+    genes = [560, 561]
+    inputs = [synth.gene_matrices("timeseries", 560, reads=20000, T=2, C=4),
+              synth.gene_matrices("timeseries", 561, reads=9000, T=2, C=12)]
+    out = run_pipeline(ctx, inputs, genes, seed=59, M=330, initial=300, gap=30)
+    check_main(out, inputs, 330, 300, 30)
+
+
 def test_cluster_tier_device_stream_step_parity(ctx):
     """A gene whose W (1.3 MB) takes the thread-block-cluster tier, device-stream mode."""
     genes = [530]
