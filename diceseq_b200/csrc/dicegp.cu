@@ -552,7 +552,7 @@ struct dicegp_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     cudaStream_t class_stream[16] = {};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[96] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join[128] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     int64_t total_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     int use_tma = 1;
 
@@ -609,7 +609,7 @@ struct dicegp_ctx {
     DevBuf<unsigned long long> dprof;
     DevBuf<unsigned long long> dctr;        // work counters of the chain kernels (ChainTab::ctr)
     size_t static_smem_wide = 0;
-    int wide_cluster_cap[4] = {0, 0, 0, 0};   // chains the wide-round kernel runs at once on clusters of 1 / 2 / 4 / 8 blocks
+    int wide_cluster_cap[5] = {0, 0, 0, 0, 0};   // chains the wide-round kernel runs at once on clusters of 1 / 2 / 4 / 8 / 16 blocks
     double last_ms = 0.0;
     int64_t last_launches = 0, last_evals = 0, last_steps = 0;
     std::vector<int32_t> hm_next_before;
@@ -658,8 +658,8 @@ ChainTab make_chain_tab(dicegp_ctx *c) {
 // that streams W from L2/HBM every step.  Each tier is further split by isoform count,
 // because the likelihood loop is compiled per C (weights f[C] in registers).
 // 0-3 resident, 4 streamed, 5-7 streamed over a cluster of 2/4/8 blocks; wide rounds (dicegp_wide.cuh): 8 = one block per
-// chain (or the cluster size of a last-stragglers pass), 9-11 = large genes on a cluster of 2/4/8 blocks in the straggler passes
-constexpr int kTiers = 12;
+// chain (or the cluster size of a last-stragglers pass), 9-12 = large genes on a cluster of 2/4/8/16 blocks in the straggler passes
+constexpr int kTiers = 13;
 constexpr int kWideTier = 8;
 constexpr int kKinds = 8;                      // kernel variants by C: generic, 2..8
 constexpr int kGroups = kTiers * kKinds;
@@ -878,7 +878,7 @@ chain_kernel_t chain_kernel_for(int kind, bool w_in_smem, bool cluster) {
 // How many chains the wide-round kernel can run at once with a cluster of `cs` blocks per chain (one block per SM;
 // clusters do not span GPCs, so this is less than SMs / cs): asked of the driver once per context.
 int wide_cluster_capacity(dicegp_ctx *c, int cs) {
-    const int slot = cs >= 8 ? 3 : (cs >= 4 ? 2 : (cs >= 2 ? 1 : 0));
+    const int slot = cs >= 16 ? 4 : (cs >= 8 ? 3 : (cs >= 4 ? 2 : (cs >= 2 ? 1 : 0)));
     if (cs <= 1) return c->sm_count;
     if (c->wide_cluster_cap[slot] == 0) {
         wide_kernel_t kern = wide_kernel_for(7, true);
@@ -892,6 +892,7 @@ int wide_cluster_capacity(dicegp_ctx *c, int cs) {
         attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            (cs > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
             cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
             cudaGetLastError();
             n = c->sm_count / cs * 3 / 4;                      // conservative guess
@@ -946,7 +947,13 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
         int tier = pick_tier(c, cls, ids[i], latency_mode);
         if (tier <= 4 && wide_eligible(c, ids[i], latency_mode)) tier = kWideTier;   // wide rejection-chain rounds
         else if (latency_mode && persistent && tier >= 5 && tier <= 7 && wide_big && wide_eligible(c, ids[i], latency_mode, tier_cluster(tier)))
+        {
             tier = kWideTier + 1 + (tier - 5);                 // large genes: the same rounds on a cluster of 2 / 4 / 8 blocks
+            // ... and of 16 (a non-portable cluster size) from 64 MB of W on: such a chain is bound by the likelihood
+            // pass alone, which shrinks with the SMs it is spread over
+            static const int64_t big16 = getenv("DICEGP_WIDE_CS16_BYTES") ? atoll(getenv("DICEGP_WIDE_CS16_BYTES")) : (64ll << 20);
+            if (tier == kWideTier + 3 && big16 > 0 && chain_wbytes(c, ids[i]) >= big16) tier = kWideTier + 4;
+        }
         if (latency_mode == 2 && tier == 4) tier = 6;          // last stragglers: a cluster of 4 blocks each
         const int k = tier * kKinds + kind_of(C);
         by_group[k].push_back(ids[i]);
@@ -1009,7 +1016,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
     int64_t launches = 0;
     int next_stream = 0;
     // big tiers first: the 1-block-per-SM and streaming launches carry most of the work
-    const int tier_order[kTiers] = {7, 6, 5, kWideTier + 3, kWideTier + 2, kWideTier + 1, kWideTier, 4, 3, 2, 1, 0};
+    const int tier_order[kTiers] = {7, 6, 5, kWideTier + 4, kWideTier + 3, kWideTier + 2, kWideTier + 1, kWideTier, 4, 3, 2, 1, 0};
     for (int to = 0; to < kTiers; ++to) {
         for (int kind_i = 0; kind_i < kKinds; ++kind_i) {
             // many isoforms first: their steps are the longest, so their chains should not be the ones that start last
@@ -1059,6 +1066,7 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
                 wide_kernel_t kern = wide_kernel_for(kind, wcs > 1);
                 DG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(c->smem_optin - c->static_smem_wide)));
+                if (wcs > 8) DG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
                 if (getenv("DICEGP_VERBOSE"))
                     fprintf(stderr, "[dicegp]   launch wide C-kind %d: %d chains, %d + %d warps, cluster %d, %zu B smem, grid %d\n",
                             kind == 0 ? 0 : kind + 1, n_ids, wp.ncw, wp.npw, wcs, smem, grid);
@@ -1378,7 +1386,7 @@ int dicegp_create(int device, dicegp_ctx **out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) goto fail;
     for (int k = 0; k < kStreams; ++k)
         if (cudaStreamCreateWithFlags(&c->class_stream[k], cudaStreamNonBlocking) != cudaSuccess) goto fail;
-    for (int k = 0; k < 96; ++k)
+    for (int k = 0; k < 128; ++k)
         if (cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) goto fail;
     if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) goto fail;
     if (cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess) goto fail;

@@ -51,7 +51,7 @@
 #define DG_WIDE_THREADS 512         // launch bound: 16 warps x 128 registers (registers come in units of 16 per thread: 17-18
                                     // warps would get 96 and spill into the task loop; measured 98 -> 90 ms on the straggler pass)
 #endif
-#define DG_WIDE_MAXCS 8             // blocks of a thread-block cluster that share one chain
+#define DG_WIDE_MAXCS 16            // blocks of a thread-block cluster that share one chain (16 = non-portable size, the largest genes)
 
 #ifdef DG_PROFILE
 // warp 0 lane 0: 0 S, 1 wait f, 2 likelihood, 3 wait partials, 4 decide + new state, 5 wait state, 6 rows; aux lane 0: 7 busy
