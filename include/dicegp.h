@@ -180,7 +180,8 @@ int dicegp_run_host_stream(dicegp_ctx *ctx, int32_t n, const int32_t *chain_ids,
  * Chains over several time points run one thread block (or cluster) each, in passes: every
  * chain to step 4096 (1024 / 2048 for batches of <= 3000 / <= 7000 chains) in throughput shapes,
  * then the stragglers with one SM each (16-candidate rounds), and -- when fewer chains than SMs are
- * left -- the survivors of every 4096 further steps on clusters of 2 / 4 / 8 SMs per chain;
+ * left -- the survivors of every 4096 further steps on clusters of 2 / 4 / 8 SMs per chain (large genes
+ * always run on clusters of 2 ... 16 SMs);
  * single-time-point chains -- the pre-runs of get_psi, static mode -- of a large enough batch run
  * one warp each to their end.
  * Which kernel advances a chain does not change its accept decisions (same stream, same
