@@ -880,7 +880,7 @@ chain_kernel_t chain_kernel_for(int kind, bool w_in_smem, bool cluster) {
 int wide_cluster_capacity(dicegp_ctx *c, int cs) {
     const int slot = cs >= 16 ? 4 : (cs >= 8 ? 3 : (cs >= 4 ? 2 : (cs >= 2 ? 1 : 0)));
     if (cs <= 1) return c->sm_count;
-    if (c->wide_cluster_cap[slot] == 0) {
+    if (c->wide_cluster_cap[slot] == 0) {                       // 0 = not asked yet, -1 = not available
         wide_kernel_t kern = wide_kernel_for(7, true);
         const int smem = (int)(c->smem_optin - c->static_smem_wide);
         int n = 0;
@@ -895,7 +895,7 @@ int wide_cluster_capacity(dicegp_ctx *c, int cs) {
             (cs > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
             cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
             cudaGetLastError();
-            n = c->sm_count / cs * 3 / 4;                      // conservative guess
+            n = cs > 8 ? -1 : c->sm_count / cs * 3 / 4;        // conservative guess; no non-portable clusters on this device
         }
         c->wide_cluster_cap[slot] = n;
     }
@@ -952,7 +952,8 @@ int run_chains(dicegp_ctx *c, const std::vector<int32_t> &ids, int n_steps, Stre
             // ... and of 16 (a non-portable cluster size) from 64 MB of W on: such a chain is bound by the likelihood
             // pass alone, which shrinks with the SMs it is spread over
             static const int64_t big16 = getenv("DICEGP_WIDE_CS16_BYTES") ? atoll(getenv("DICEGP_WIDE_CS16_BYTES")) : (64ll << 20);
-            if (tier == kWideTier + 3 && big16 > 0 && chain_wbytes(c, ids[i]) >= big16) tier = kWideTier + 4;
+            if (tier == kWideTier + 3 && big16 > 0 && chain_wbytes(c, ids[i]) >= big16 && wide_cluster_capacity(c, 16) > 0)
+                tier = kWideTier + 4;
         }
         if (latency_mode == 2 && tier == 4) tier = 6;          // last stragglers: a cluster of 4 blocks each
         const int k = tier * kKinds + kind_of(C);
