@@ -774,14 +774,13 @@ __device__ void run_chain_wide(const GeneTab &gt, const ChainTab &ct, const Stre
         DG_WTICK(5);
         if (nd > 0 && lead) {
             const double *sold = state + cur * 2 * CT, *snw = state + (cur ^ 1) * 2 * CT;
-            const int total = nd * rowlen;
-            for (int idx = tid; idx < total; idx += nthreads) {
-                const int d = idx / rowlen, col = idx - d * rowlen;
+            // one warp per row: the row address is formed once, the lanes walk the columns (coalesced, no divisions)
+            for (int d = warp; d < nd; d += nwarps) {
                 const bool nw_ = d == first;
                 const double *sb = nw_ ? snw : sold;
-                const double v = col < 2 * CT ? sb[col] : (col == 2 * CT ? (nw_ ? P_new : P_now) : (nw_ ? L_new : L_now));
                 double *row = ct.trace + __double_as_longlong(bc[32 + d]) + (size_t)((m + d) & pmask) * rowlen;
-                row[col] = v;                                                // Psi_all / Y_all / Pro_all / Lik_all [m+d]  (:362-366)
+                for (int col = lane; col < rowlen; col += 32)                    // Psi_all / Y_all / Pro_all / Lik_all [m+d]  (:362-366)
+                    row[col] = col < 2 * CT ? sb[col] : (col == 2 * CT ? (nw_ ? P_new : P_now) : (nw_ ? L_new : L_now));
             }
         }
         if (first >= 0) { cur ^= 1; P_now = P_new; L_now = L_new; if (!init) ++cnt; }
